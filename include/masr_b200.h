@@ -1,0 +1,136 @@
+/* masr_b200 — C ABI of the B200-native MASR inference hot path.
+ *
+ * The reference (yeyupiaoling/MASR) is pure Python and has NO FFI of its own: its hot path is
+ * `MASRPredictor.predict / predict_stream` (masr/predict.py:167,237) -> `AudioFeaturizer.featurize`
+ * (masr/data_utils/featurizer/audio_featurizer.py:37) -> `InferencePredictor.predict[_chunk_*]`
+ * (masr/infer_utils/inference_predictor.py:52,80) -> TorchScript `get_encoder_out[_chunk]`
+ * (masr/model_utils/conformer/model.py:152,169) -> `greedy_decoder` (masr/decoders/ctc_greedy_decoder.py:6).
+ * Every library call on that path (torchaudio kaldi.fbank, ATen linear/conv/layer_norm/softmax, numpy
+ * argmax) is replaced by one of the entry points below; the Python host code in `masr_b200/` binds them
+ * with ctypes and keeps the reference's class/method interface.  INTEGRATION.md shows the stub a MASR
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (caller-owned, allocated e.g. with torch.empty(device='cuda'))
+ *     unless its name ends in `_host`; nothing is allocated, freed or retained by the library;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it;
+ *   - float32 everywhere ("f32" suffix), row-major, leading dimensions (`ld*`) in elements;
+ *   - returns MASR_OK (0) or an error code; `masr_last_error()` has the message (thread-local);
+ *   - there is no CPU fallback: without an sm_100 device the calls fail.
+ */
+#ifndef MASR_B200_H_
+#define MASR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MASR_ABI_VERSION 1
+
+enum {
+    MASR_OK = 0,
+    MASR_ERR_INVALID_ARGUMENT = 10001,
+    MASR_ERR_UNSUPPORTED_DEVICE = 10002,
+    MASR_ERR_INTERNAL = 10003,
+};
+
+/* per-utterance status flags written by masr_wave_gain_f32 */
+enum { MASR_STATUS_GAIN_EXCEEDED = 1 };
+
+/* GEMM epilogues */
+enum {
+    MASR_EPI_BIAS = 0,      /* C = A.W^T + bias                                              */
+    MASR_EPI_BIAS_SILU = 1, /* C = silu(A.W^T + bias)                  positionwise.py:37    */
+    MASR_EPI_BIAS_RELU = 2, /* C = relu(A.W^T + bias)                  subsampling.py:82,84  */
+    MASR_EPI_BIAS_GLU = 3,  /* C[:, j] = v[2j] * sigmoid(v[2j+1])      convolution.py:118    */
+    MASR_EPI_BIAS_SCALE = 4,/* C = (A.W^T + bias) * alpha              embedding.py:98       */
+    MASR_EPI_RESIDUAL = 5,  /* C = residual + alpha * (A.W^T + bias)   encoder.py:117,131,145,155 */
+};
+
+const char* masr_last_error(void);
+int masr_abi_version(void);
+int masr_check_device(void);
+
+/* ---- audio front-end -------------------------------------------------------------------------- */
+
+/* Bytes of scratch masr_wave_gain_f32 needs for B utterances of at most max_samples samples. */
+int masr_fbank_workspace_bytes(int B, int64_t max_samples, int64_t* bytes_host);
+
+/* dB normalisation factor per utterance: AudioSegment.normalize / rms_db / gain_db
+ * (masr/data_utils/audio.py:287-304,519-529,256-264).  wave: packed float32 samples in [-1,1);
+ * offsets: int64[B+1] sample offsets.  gain[b] = 10^((target_db - 10*log10(mean(x^2)))/20);
+ * status[b] = MASR_STATUS_GAIN_EXCEEDED where the reference raises ValueError (gain > max_gain_db). */
+int masr_wave_gain_f32(const float* wave, const int64_t* offsets, int B, int64_t max_samples, float target_db,
+                       float max_gain_db, float* gain, int* status, void* workspace, void* stream);
+
+/* AudioSegment.to('int16') + torchaudio.compliance.kaldi.fbank(num_mel_bins=80, frame_length=25,
+ * frame_shift=10, dither=0, sample_frequency=16000) (audio.py:244-254,549-574;
+ * audio_featurizer.py:120-138; torchaudio kaldi.py:514-645).  gain may be NULL (no dB normalisation).
+ * feats: [B, Fmax, 80] raw log-mel, rows >= the utterance's frame count are zero;
+ * num_frames[b] = 1 + (n_b - 400) / 160 (0 if n_b < 400), may be NULL. */
+int masr_fbank_f32(const float* wave, const int64_t* offsets, const float* gain, int B, int Fmax, float* feats,
+                   int* num_frames, void* stream);
+
+/* ---- encoder building blocks ------------------------------------------------------------------ */
+
+/* GlobalCMVN (masr/model_utils/utils/cmvn.py:29-31) + Conv2d(1,C,3,2) + ReLU
+ * (masr/model_utils/conformer/subsampling.py:81-82).  feats [B,Fmax,idim] -> out [B,F1max,W1,C]
+ * channels-last; w1 [C,1,3,3] as stored by the reference; mean/istd may both be NULL. */
+int masr_conv1_cmvn_relu_f32(const float* feats, const float* mean, const float* istd, const float* w1,
+                             const float* b1, float* out, int B, int Fmax, int idim, int F1max, int W1, int C,
+                             void* stream);
+
+/* Conv2d(C,C,3,2) + ReLU (subsampling.py:83-84) as an implicit GEMM over the channels-last conv-1
+ * activation.  w2p [C, 3, 3, C] = reference weight [co,ci,kh,kw] permuted to [co,kh,kw,ci].
+ * out [B, T2max, W2, C] (== the [B*T2max, W2*C] input of the `out` linear, subsampling.py:110). */
+int masr_conv2_s2_relu_f32(const float* c1, const float* w2p, const float* b2, float* out, int B, int F1max,
+                           int W1, int T2max, int W2, int C, void* stream);
+
+/* torch.nn.functional.linear / Conv1d(k=1) with a fused epilogue: C[M,N] = epi(A[M,K] . W[N,K]^T).
+ * K % 16 == 0, lda % 4 == 0.  For MASR_EPI_BIAS_GLU the weight/bias rows are interleaved
+ * (row 2j = value j, row 2j+1 = gate j) and C has N/2 columns. */
+int masr_gemm_f32(const float* A, int64_t lda, const float* W, const float* bias, const float* residual,
+                  int64_t ldr, float* C, int64_t ldc, int M, int N, int K, int epilogue, float alpha,
+                  void* stream);
+
+/* torch.nn.LayerNorm(D, eps) over the last dimension (encoder.py:64-72; convolution.py:66). */
+int masr_layernorm_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* y, int64_t ldy,
+                       int M, int D, float eps, void* stream);
+
+/* RelPositionMultiHeadedAttention core (masr/model_utils/conformer/attention.py:230-251,107-118):
+ * Q rows (b*q_bstride + i), K/V rows (b*k_bstride + j), head h at column h*d_k; P [>=max klen, ldp] =
+ * linear_pos(pos_emb) rows aligned with key index j; pos_u/pos_v [H,d_k]; O like Q.
+ * q_lens/k_lens int32[B]: valid queries / keys per utterance (rows beyond q_lens are written as 0). */
+int masr_relpos_attention_f32(const float* Q, int64_t ldq, int64_t q_bstride, const float* K, const float* V,
+                              int64_t ldk, int64_t k_bstride, const float* P, int64_t ldp, const float* pos_u,
+                              const float* pos_v, float* O, int64_t ldo, int64_t o_bstride, const int* q_lens,
+                              const int* k_lens, int B, int H, int d_k, int max_q, void* stream);
+
+/* ConvolutionModule middle (masr/model_utils/conformer/convolution.py:121-126): depthwise Conv1d(k)
+ * -> LayerNorm(C) -> SiLU.  y[b,t,:] for t < out_rows from g[b, t - lpad + k, :], k < kernel_size;
+ * g rows < 0 read pad_vec (NULL = 0), rows >= in_lens[b] read 0.  w [C,k] (reference [C,1,k]). */
+int masr_dwconv_ln_silu_f32(const float* g, int64_t ldg, int64_t g_bstride, const float* w, const float* bias,
+                            const float* ln_gamma, const float* ln_beta, const float* pad_vec, float* y,
+                            int64_t ldy, int64_t y_bstride, const int* in_lens, int B, int C, int kernel_size,
+                            int lpad, int out_rows, float eps, void* stream);
+
+/* ---- CTC head / greedy decode ------------------------------------------------------------------- */
+
+/* softmax statistics of CTCLoss.softmax (masr/model_utils/loss/ctc.py:70) fused with the argmax of
+ * greedy_decoder (masr/decoders/ctc_greedy_decoder.py:21-22): ids[m] = first argmax_v, maxp[m] =
+ * softmax(logits[m])[ids[m]].  probs (optional, may be NULL): full posterior [M, ldp]. */
+int masr_ctc_frame_argmax_f32(const float* logits, int64_t ldl, int M, int V, int* ids, float* maxp, float* probs,
+                              int64_t ldp, void* stream);
+
+/* greedy_decoder's collapse (ctc_greedy_decoder.py:23-30): per utterance b over frames t < lens[b]
+ * (rows b*bstride + t): tokens = ids with consecutive repeats merged and `blank` dropped;
+ * psum/pcount = float32 left-to-right sum / count of maxp over non-blank frames (score = 100*psum/pcount). */
+int masr_ctc_greedy_collapse(const int* ids, const float* maxp, int64_t bstride, const int* lens, int B, int blank,
+                             int* tokens, int64_t tok_stride, int* ntok, float* psum, int* pcount, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MASR_B200_H_ */

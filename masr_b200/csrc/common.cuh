@@ -1,0 +1,55 @@
+// Shared device/host helpers for the masr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/masr_b200.h"
+
+namespace masr {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_last_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+#define MASR_REQUIRE(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            masr::set_last_error(__VA_ARGS__);  \
+            return MASR_ERR_INVALID_ARGUMENT;   \
+        }                                       \
+    } while (0)
+
+// ---- warp primitives ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// IEEE-accurate SiLU: x * sigmoid(x), the way ATen computes it (x / (1 + exp(-x))).
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// 128-bit streaming global accesses (guide: Guideline 13).
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+}  // namespace masr

@@ -1,0 +1,428 @@
+"""Device engine: drives the sm_100a kernels of ``libmasr_b200.so`` over packed weights.
+
+This is the object that replaces the reference's ``InferencePredictor`` + TorchScript module
+(masr/infer_utils/inference_predictor.py:10-102, masr/model_utils/conformer/model.py:152-190) and
+the featurizer / greedy decoder on either side of it.  PyTorch is used for device memory, streams
+and (elsewhere) ``torch.distributed`` only; every arithmetic operation on the path is one of the
+ABI calls declared in ``include/masr_b200.h``.
+
+Batched entry points are *additive* (the reference API is single-utterance, predict.py:183-187);
+each row of a ragged batch is computed exactly as if it were alone (B=1 semantics).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_BIAS_GLU, EPI_BIAS_SCALE, EPI_BIAS_SILU, EPI_RESIDUAL, call
+from .weights import ConformerWeights, load_state_dict, pack_conformer
+
+FRAME_LEN, FRAME_SHIFT, NUM_MEL = 400, 160, 80
+
+
+def num_frames(num_samples: int) -> int:
+    """torchaudio kaldi.py:63-67 (snip_edges)."""
+    return 0 if num_samples < FRAME_LEN else 1 + (num_samples - FRAME_LEN) // FRAME_SHIFT
+
+
+def subsampled_len(frames: int) -> int:
+    """Conv2dSubsampling4 output length: two valid 3x1 stride-2 convs (subsampling.py:81-84)."""
+    return max(0, ((frames - 1) // 2 - 1) // 2)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class GreedyResult:
+    tokens: List[List[int]]     # collapsed, blank-free ids per utterance
+    scores: List[float]         # reference `score` (0..100)
+    frame_ids: Optional[np.ndarray] = None   # [B, Tmax] raw per-frame argmax (for parity tests)
+    frame_lens: Optional[np.ndarray] = None
+    status: Optional[np.ndarray] = None      # per-utterance front-end status flags
+
+
+class ConformerEngine:
+    """Conformer (configs/conformer.yml) inference on one B200."""
+
+    def __init__(self, weights_src, streaming: bool = True, device: str = "cuda", max_len: int = 5000):
+        if not torch.cuda.is_available():
+            raise _lib.MasrB200Error("masr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        torch.cuda.set_device(self.device)
+        call("masr_check_device")
+        sd = load_state_dict(weights_src)
+        self.w: ConformerWeights = pack_conformer(sd, self.device, max_len)
+        self.causal = bool(streaming)      # model.py:35-39: streaming -> causal conv + dynamic chunk
+        self.d, self.h = self.w.d_model, self.w.heads
+        self.dk = self.d // self.h
+        self.V = self.w.vocab
+        self.Vpad = (self.V + 15) // 16 * 16
+        self.f2 = ((self.w.idim - 1) // 2 - 1) // 2
+        self.w1_cols = (self.w.idim - 1) // 2
+        self._ws: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+        self.launches = 0
+        self._precompute_pos()
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _gemm(self, A, lda, W, bias, C, ldc, M, N, K, epi=EPI_BIAS, alpha=1.0, residual=None, ldr=0):
+        call("masr_gemm_f32", _p(A), lda, _p(W), _p(bias), _p(residual), ldr, _p(C), ldc, M, N, K, epi, alpha,
+             self._stream())
+        self.launches += 1
+
+    def _ln(self, x, gb, y, M, ld=None):
+        ld = self.d if ld is None else ld
+        call("masr_layernorm_f32", _p(x), ld, _p(gb[0]), _p(gb[1]), _p(y), ld, M, self.d, 1e-5, self._stream())
+        self.launches += 1
+
+    def _precompute_pos(self):
+        """linear_pos(pe) for every layer: input-independent (attention.py:228), done once on the GPU."""
+        for L in self.w.layers:
+            L.ptab = torch.empty(self.w.max_len, self.d, device=self.device, dtype=torch.float32)
+            self._gemm(self.w.pe, self.d, L.wpos, None, L.ptab, self.d, self.w.max_len, self.d, self.d)
+        torch.cuda.synchronize(self.device)
+
+    def _workspace(self, B: int, Fmax: int) -> Dict[str, torch.Tensor]:
+        key = (B, Fmax)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev, f32 = self.device, torch.float32
+        F1 = (Fmax - 1) // 2
+        T = subsampled_len(Fmax)
+        M = B * T
+        d = self.d
+        ws = {
+            "c1": torch.empty(B * F1 * self.w1_cols * d, device=dev, dtype=f32),
+            "c2": torch.empty(max(1, M) * self.f2 * d, device=dev, dtype=f32),
+            "x": torch.empty(max(1, M), d, device=dev, dtype=f32),
+            "t0": torch.empty(max(1, M), d, device=dev, dtype=f32),
+            "t1": torch.empty(max(1, M), d, device=dev, dtype=f32),
+            "g": torch.empty(max(1, M), d, device=dev, dtype=f32),
+            "hid": torch.empty(max(1, M), self.w.ffn, device=dev, dtype=f32),
+            "qkv": torch.empty(max(1, M), 3 * d, device=dev, dtype=f32),
+            "logits": torch.empty(max(1, M), self.Vpad, device=dev, dtype=f32),
+            "ids": torch.empty(max(1, M), device=dev, dtype=torch.int32),
+            "maxp": torch.empty(max(1, M), device=dev, dtype=f32),
+            "tokens": torch.empty(B, max(1, T), device=dev, dtype=torch.int32),
+            "ntok": torch.empty(B, device=dev, dtype=torch.int32),
+            "psum": torch.empty(B, device=dev, dtype=f32),
+            "pcount": torch.empty(B, device=dev, dtype=torch.int32),
+        }
+        if len(self._ws) > 8:
+            self._ws.clear()
+        self._ws[key] = ws
+        return ws
+
+    # ---- front-end ---------------------------------------------------------------------------
+    def fbank(self, waves: Sequence[np.ndarray], use_db_normalization: bool = True, target_db: float = -20.0,
+              wave_dev: Optional[torch.Tensor] = None, offsets_dev: Optional[torch.Tensor] = None,
+              lengths: Optional[Sequence[int]] = None):
+        """float32 waveforms in [-1,1) -> (feats [B,Fmax,80] on device, frame counts, status flags).
+
+        Either host arrays (copied through pinned memory) or an already packed device buffer
+        (``wave_dev`` float32[total], ``offsets_dev`` int64[B+1], ``lengths``)."""
+        if wave_dev is None:
+            lengths = [int(w.shape[0]) for w in waves]
+            offs = np.zeros(len(waves) + 1, np.int64)
+            np.cumsum(lengths, out=offs[1:])
+            total = int(offs[-1])
+            host = torch.empty(max(1, total), dtype=torch.float32, pin_memory=True)
+            hv = host.numpy()
+            for i, w in enumerate(waves):
+                hv[offs[i]:offs[i + 1]] = w
+            wave_dev = host.to(self.device, non_blocking=True)
+            offsets_dev = torch.from_numpy(offs).pin_memory().to(self.device, non_blocking=True)
+        B = len(lengths)
+        frames = [num_frames(n) for n in lengths]
+        Fmax = max(frames) if frames else 0
+        max_samples = max(lengths) if lengths else 0
+        dev = self.device
+        feats = torch.empty(B, max(1, Fmax), NUM_MEL, device=dev, dtype=torch.float32)
+        status = torch.zeros(B, device=dev, dtype=torch.int32)
+        gain = None
+        st = self._stream()
+        if use_db_normalization:
+            nbytes = _lib.C.c_int64(0)
+            call("masr_fbank_workspace_bytes", B, max_samples, _lib.C.byref(nbytes))
+            scratch = torch.empty(max(8, nbytes.value), device=dev, dtype=torch.uint8)
+            gain = torch.empty(B, device=dev, dtype=torch.float32)
+            call("masr_wave_gain_f32", _p(wave_dev), _p(offsets_dev), B, max_samples, float(target_db), 300.0,
+                 _p(gain), _p(status), _p(scratch), st)
+            self.launches += 2
+        if Fmax > 0:
+            call("masr_fbank_f32", _p(wave_dev), _p(offsets_dev), _p(gain), B, Fmax, _p(feats), None, st)
+            self.launches += 1
+        return feats, frames, status
+
+    # ---- encoder -----------------------------------------------------------------------------
+    def encode(self, feats: torch.Tensor, feat_lens: Sequence[int]):
+        """feats [B,Fmax,80] raw log-mel (device) -> (enc [B*Tmax, d] after `after_norm`, out lens, Tmax, ws)."""
+        w = self.w
+        B, Fmax = feats.shape[0], feats.shape[1]
+        F1 = (Fmax - 1) // 2
+        T = subsampled_len(Fmax)
+        tl = [subsampled_len(int(f)) for f in feat_lens]
+        ws = self._workspace(B, Fmax)
+        if T == 0:
+            return ws["x"][:0], tl, 0, ws
+        M, d, st = B * T, self.d, self._stream()
+        tlens = torch.tensor(tl, dtype=torch.int32).pin_memory().to(self.device, non_blocking=True)
+        ws["tlens"] = tlens
+        # Conv2dSubsampling4 (+ CMVN) -> x * sqrt(d)
+        call("masr_conv1_cmvn_relu_f32", _p(feats), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w), _p(w.conv1_b),
+             _p(ws["c1"]), B, Fmax, w.idim, F1, self.w1_cols, d, st)
+        call("masr_conv2_s2_relu_f32", _p(ws["c1"]), _p(w.conv2_w), _p(w.conv2_b), _p(ws["c2"]), B, F1, self.w1_cols, T,
+             self.f2, d, st)
+        self.launches += 2
+        x, t0, t1, g, hid, qkv = ws["x"], ws["t0"], ws["t1"], ws["g"], ws["hid"], ws["qkv"]
+        self._gemm(ws["c2"], self.f2 * d, w.embed_w, w.embed_b, x, d, M, d, self.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5)
+        lpad = (w.kernel - 1) if self.causal else (w.kernel - 1) // 2
+        for L in w.layers:
+            # macaron FFN: x += 0.5 * W2 silu(W1 LN(x))
+            self._ln(x, L.ln_ffm, t0, M)
+            self._gemm(t0, d, L.ffm[0], L.ffm[1], hid, w.ffn, M, w.ffn, d, EPI_BIAS_SILU)
+            self._gemm(hid, w.ffn, L.ffm[2], L.ffm[3], x, d, M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d)
+            # rel-pos MHSA
+            self._ln(x, L.ln_mha, t0, M)
+            self._gemm(t0, d, L.wqkv, L.bqkv, qkv, 3 * d, M, 3 * d, d)
+            call("masr_relpos_attention_f32", _p(qkv), 3 * d, T, qkv.data_ptr() + 4 * d, qkv.data_ptr() + 8 * d,
+                 3 * d, T, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), _p(t1), d, T, _p(tlens), _p(tlens), B, self.h,
+                 self.dk, T, st)
+            self.launches += 1
+            self._gemm(t1, d, L.wo, L.bo, x, d, M, d, d, EPI_RESIDUAL, 1.0, x, d)
+            # convolution module
+            self._ln(x, L.ln_conv, t0, M)
+            self._gemm(t0, d, L.pw1, L.pw1_b, g, d, M, 2 * d, d, EPI_BIAS_GLU)
+            call("masr_dwconv_ln_silu_f32", _p(g), d, T, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]),
+                 _p(L.glu_pad) if self.causal else None, _p(t1), d, T, _p(tlens), B, d, w.kernel, lpad, T, 1e-5, st)
+            self.launches += 1
+            self._gemm(t1, d, L.pw2, L.pw2_b, x, d, M, d, d, EPI_RESIDUAL, 1.0, x, d)
+            # FFN
+            self._ln(x, L.ln_ff, t0, M)
+            self._gemm(t0, d, L.ff[0], L.ff[1], hid, w.ffn, M, w.ffn, d, EPI_BIAS_SILU)
+            self._gemm(hid, w.ffn, L.ff[2], L.ff[3], x, d, M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d)
+            self._ln(x, L.ln_final, x, M)
+        self._ln(x, w.after_norm, t0, M)
+        return t0[:M], tl, T, ws
+
+    # ---- CTC head ----------------------------------------------------------------------------
+    def ctc_logits(self, enc: torch.Tensor, ws) -> torch.Tensor:
+        M = enc.shape[0]
+        self._gemm(enc, self.d, self.w.ctc_w, self.w.ctc_b, ws["logits"], self.Vpad, M, self.V, self.d)
+        return ws["logits"]
+
+    def ctc_greedy(self, enc: torch.Tensor, out_lens: Sequence[int], T: int, ws, want_probs: bool = False):
+        """-> device tensors (tokens [B,T], ntok, psum, pcount, ids [B*T], probs or None)."""
+        B = len(out_lens)
+        M = B * T
+        st = self._stream()
+        logits = self.ctc_logits(enc, ws)
+        probs = torch.empty(M, self.V, device=self.device, dtype=torch.float32) if want_probs else None
+        call("masr_ctc_frame_argmax_f32", _p(logits), self.Vpad, M, self.V, _p(ws["ids"]), _p(ws["maxp"]), _p(probs),
+             self.V, st)
+        call("masr_ctc_greedy_collapse", _p(ws["ids"]), _p(ws["maxp"]), T, _p(ws["tlens"]), B, 0, _p(ws["tokens"]),
+             ws["tokens"].shape[1], _p(ws["ntok"]), _p(ws["psum"]), _p(ws["pcount"]), st)
+        self.launches += 2
+        return probs
+
+    # ---- public batched entry points -----------------------------------------------------------
+    def transcribe(self, waves: Sequence[np.ndarray], use_db_normalization: bool = True, target_db: float = -20.0,
+                   return_frames: bool = False) -> GreedyResult:
+        """Host float32 waveforms -> greedy token ids + scores.  One H2D copy in, a few KB out."""
+        feats, frames, status = self.fbank(waves, use_db_normalization, target_db)
+        return self.transcribe_features(feats, frames, status, return_frames)
+
+    def transcribe_features(self, feats, frames, status=None, return_frames: bool = False) -> GreedyResult:
+        B = feats.shape[0]
+        enc, tl, T, ws = self.encode(feats, frames)
+        if T == 0:
+            return GreedyResult([[] for _ in range(B)], [0.0] * B, None, np.zeros(B, np.int32),
+                                None if status is None else status.cpu().numpy())
+        self.ctc_greedy(enc, tl, T, ws)
+        # one small D2H: tokens + counters (+ raw frame ids for tests)
+        tok = ws["tokens"].cpu().numpy()
+        ntok = ws["ntok"].cpu().numpy()
+        psum = ws["psum"].cpu().numpy()
+        pcnt = ws["pcount"].cpu().numpy()
+        tokens = [tok[b, :ntok[b]].tolist() for b in range(B)]
+        scores = [greedy_score(psum[b], pcnt[b]) for b in range(B)]
+        fid = ws["ids"][:B * T].view(B, T).cpu().numpy() if return_frames else None
+        return GreedyResult(tokens, scores, fid, np.asarray(tl, np.int32),
+                            None if status is None else status.cpu().numpy())
+
+    def posteriors(self, feats_host: np.ndarray, feat_lens: Sequence[int]) -> np.ndarray:
+        """The ``InferencePredictor.predict`` seam (inference_predictor.py:52-64): raw features
+        np[B,F,80] + lengths -> CTC posteriors np[B,T,V]."""
+        feats = torch.from_numpy(np.ascontiguousarray(feats_host, dtype=np.float32)).to(self.device)
+        B = feats.shape[0]
+        enc, tl, T, ws = self.encode(feats, feat_lens)
+        if T == 0:
+            return np.zeros((B, 0, self.V), np.float32)
+        probs = self.ctc_greedy(enc, tl, T, ws, want_probs=True)
+        return probs.view(B, T, self.V).cpu().numpy()
+
+
+    # ---- streaming (chunk) path -----------------------------------------------------------------
+    def new_stream(self) -> "ConformerStream":
+        return ConformerStream(self)
+
+    def encode_chunk(self, feats_chunk: torch.Tensor, st: "ConformerStream", required_cache_size: int = -1,
+                     want_probs: bool = False):
+        """``ConformerEncoder.forward_chunk`` + CTC softmax for ONE stream (encoder.py:348-420,
+        model.py:169-190): feats_chunk [n<=67, 80] raw log-mel on device -> per-frame (ids, max-prob)
+        device tensors of length c = ((n-1)//2-1)//2 (+ posteriors [c,V] if asked).  Updates the
+        stream's attention / convolution caches and ``offset`` like inference_predictor.py:84-93."""
+        w, d, s = self.w, self.d, self._stream()
+        n = int(feats_chunk.shape[0])
+        c = subsampled_len(n)
+        if c == 0:
+            return None
+        if not self.causal:
+            raise Exception("chunk decoding needs a streaming (causal) model")
+        F1 = (n - 1) // 2
+        lorder = w.kernel - 1
+        cache_t1 = st.cache_len
+        key_size = cache_t1 + c
+        if st.offset + c >= w.max_len:    # embedding.py:95-97
+            raise AssertionError("offset: {} + x.shape[1]: {} is larger than the max_len: {}".format(st.offset, c, w.max_len))
+        st.reserve(key_size)
+        ws = st.ws
+        call("masr_conv1_cmvn_relu_f32", _p(feats_chunk), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w), _p(w.conv1_b),
+             _p(ws["c1"]), 1, n, w.idim, F1, self.w1_cols, d, s)
+        call("masr_conv2_s2_relu_f32", _p(ws["c1"]), _p(w.conv2_w), _p(w.conv2_b), _p(ws["c2"]), 1, F1, self.w1_cols, c,
+             self.f2, d, s)
+        self.launches += 2
+        x, t0, t1, g, hid, q, xcat = ws["x"], ws["t0"], ws["t1"], ws["g"], ws["hid"], ws["q"], ws["xcat"]
+        self._gemm(ws["c2"], self.f2 * d, w.embed_w, w.embed_b, x, d, c, d, self.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5)
+        ws["qlen"].fill_(c)
+        ws["klen"].fill_(key_size)
+        ws["clen"].fill_(lorder + c)
+        pos_start = st.offset - cache_t1      # encoder.py:384
+        for li, L in enumerate(w.layers):
+            self._ln(x, L.ln_ffm, t0, c)
+            self._gemm(t0, d, L.ffm[0], L.ffm[1], hid, w.ffn, c, w.ffn, d, EPI_BIAS_SILU)
+            self._gemm(hid, w.ffn, L.ffm[2], L.ffm[3], x, d, c, d, w.ffn, EPI_RESIDUAL, 0.5, x, d)
+            self._ln(x, L.ln_mha, t0, c)
+            kv = st.kv[li]                                             # [cap, 2d] rows = key positions
+            self._gemm(t0, d, L.wqkv, L.bqkv, q, d, c, d, d)           # q
+            call("masr_gemm_f32", _p(t0), d, L.wqkv.data_ptr() + 4 * d * d, L.bqkv.data_ptr() + 4 * d, None, 0,
+                 kv.data_ptr() + 4 * (st.cache_start + cache_t1) * 2 * d, 2 * d, c, 2 * d, d, EPI_BIAS, 1.0, s)  # k|v appended
+            kbase = kv.data_ptr() + 4 * st.cache_start * 2 * d
+            call("masr_relpos_attention_f32", _p(q), d, 0, kbase, kbase + 4 * d, 2 * d, 0,
+                 L.ptab.data_ptr() + 4 * pos_start * d, d, _p(L.pos_u), _p(L.pos_v), _p(t1), d, 0, _p(ws["qlen"]),
+                 _p(ws["klen"]), 1, self.h, self.dk, c, s)
+            self.launches += 2
+            self._gemm(t1, d, L.wo, L.bo, x, d, c, d, d, EPI_RESIDUAL, 1.0, x, d)
+            # conv module over [cache ++ chunk] (convolution.py:101-109); zero cache == the reference's zero pad
+            xc = xcat[li]
+            call("masr_layernorm_f32", _p(x), d, _p(L.ln_conv[0]), _p(L.ln_conv[1]), xc.data_ptr() + 4 * lorder * d, d, c,
+                 d, 1e-5, s)
+            self.launches += 1
+            self._gemm(xc, d, L.pw1, L.pw1_b, g, d, lorder + c, 2 * d, d, EPI_BIAS_GLU)
+            call("masr_dwconv_ln_silu_f32", _p(g), d, 0, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]), None, _p(t1), d, 0,
+                 _p(ws["clen"]), 1, d, w.kernel, 0, c, 1e-5, s)
+            self.launches += 1
+            # new cnn cache = last `lorder` rows of [cache ++ chunk]; overlapping move -> go through a scratch
+            ws["ctmp"][:lorder].copy_(xc[c:c + lorder])
+            xc[:lorder].copy_(ws["ctmp"][:lorder])
+            self._gemm(t1, d, L.pw2, L.pw2_b, x, d, c, d, d, EPI_RESIDUAL, 1.0, x, d)
+            self._ln(x, L.ln_ff, t0, c)
+            self._gemm(t0, d, L.ff[0], L.ff[1], hid, w.ffn, c, w.ffn, d, EPI_BIAS_SILU)
+            self._gemm(hid, w.ffn, L.ff[2], L.ff[3], x, d, c, d, w.ffn, EPI_RESIDUAL, 0.5, x, d)
+            self._ln(x, L.ln_final, x, c)
+        self._ln(x, w.after_norm, t0, c)
+        self._gemm(t0, d, w.ctc_w, w.ctc_b, ws["logits"], self.Vpad, c, self.V, d)
+        probs = torch.empty(c, self.V, device=self.device, dtype=torch.float32) if want_probs else None
+        call("masr_ctc_frame_argmax_f32", _p(ws["logits"]), self.Vpad, c, self.V, _p(ws["ids"]), _p(ws["maxp"]), _p(probs),
+             self.V, s)
+        self.launches += 1
+        # cache bookkeeping (encoder.py:397-402, inference_predictor.py:93)
+        if required_cache_size < 0:
+            keep = key_size
+        elif required_cache_size == 0:
+            keep = 0
+        else:
+            keep = min(key_size, required_cache_size)
+        st.cache_start += key_size - keep
+        st.cache_len = keep
+        st.offset += c
+        return ws["ids"][:c], ws["maxp"][:c], probs
+
+
+class ConformerStream:
+    """Per-stream state the reference keeps on ``InferencePredictor`` (inference_predictor.py:45-49,
+    97-102): attention K|V cache per layer, conv-module left context per layer, output offset."""
+
+    MAX_CHUNK_FRAMES = 67 + 64      # feature frames accepted per chunk call
+
+    def __init__(self, eng: ConformerEngine):
+        self.eng = eng
+        dev, f32, d, w = eng.device, torch.float32, eng.d, eng.w
+        nl = len(w.layers)
+        lorder = w.kernel - 1
+        cmax = subsampled_len(self.MAX_CHUNK_FRAMES)
+        F1 = (self.MAX_CHUNK_FRAMES - 1) // 2
+        self.cap = 0
+        self.kv: List[torch.Tensor] = [torch.empty(0, 2 * d, device=dev, dtype=f32) for _ in range(nl)]
+        self.ws = {
+            "c1": torch.empty(F1 * eng.w1_cols * d, device=dev, dtype=f32),
+            "c2": torch.empty(cmax * eng.f2 * d, device=dev, dtype=f32),
+            "x": torch.empty(cmax, d, device=dev, dtype=f32),
+            "t0": torch.empty(cmax, d, device=dev, dtype=f32),
+            "t1": torch.empty(cmax, d, device=dev, dtype=f32),
+            "q": torch.empty(cmax, d, device=dev, dtype=f32),
+            "g": torch.empty(cmax + lorder, d, device=dev, dtype=f32),
+            "hid": torch.empty(cmax, w.ffn, device=dev, dtype=f32),
+            "xcat": torch.zeros(nl, cmax + lorder, d, device=dev, dtype=f32),
+            "ctmp": torch.empty(max(1, lorder), d, device=dev, dtype=f32),
+            "logits": torch.empty(cmax, eng.Vpad, device=dev, dtype=f32),
+            "ids": torch.empty(cmax, device=dev, dtype=torch.int32),
+            "maxp": torch.empty(cmax, device=dev, dtype=f32),
+            "qlen": torch.zeros(1, device=dev, dtype=torch.int32),
+            "klen": torch.zeros(1, device=dev, dtype=torch.int32),
+            "clen": torch.zeros(1, device=dev, dtype=torch.int32),
+        }
+        self.reset()
+
+    def reset(self):
+        """``InferencePredictor.reset_stream`` (inference_predictor.py:97-102)."""
+        self.offset = 0
+        self.cache_len = 0
+        self.cache_start = 0
+        self.ws["xcat"].zero_()
+
+    def reserve(self, key_size: int):
+        """Make room for ``key_size`` key rows after ``cache_start`` (geometric growth; compaction
+        when a bounded cache has slid far enough)."""
+        need = self.cache_start + key_size
+        if need <= self.cap:
+            return
+        d2 = 2 * self.eng.d
+        new_cap = max(256, 2 * (self.cache_len + key_size))
+        for i, old in enumerate(self.kv):
+            buf = torch.empty(new_cap, d2, device=self.eng.device, dtype=torch.float32)
+            if self.cache_len:
+                buf[:self.cache_len].copy_(old[self.cache_start:self.cache_start + self.cache_len])
+            self.kv[i] = buf
+        self.cap = new_cap
+        self.cache_start = 0
+
+
+def greedy_score(psum: np.float32, pcount: int) -> float:
+    """``float(sum(list) / len(list)) * 100.0`` with float32 scalars (ctc_greedy_decoder.py:28-30)."""
+    if int(pcount) == 0:
+        return 0
+    return float(np.float32(np.float32(psum) / np.float32(int(pcount)))) * 100.0

@@ -1,0 +1,166 @@
+"""Deterministic synthetic fixtures: weights, vocabulary, CMVN statistics and audio.
+
+The reference ships no trained weights, vocabulary or golden vectors, so
+every parity test, the smoke test and ``bench.py`` run on synthetic data that can be
+regenerated bit-identically on any machine from a seed (``numpy.random.Generator`` streams
+are stable across platforms).  The tensors follow the *reference's* ``state_dict`` layout
+(key names and shapes probed from ``ConformerModel(...).state_dict()``, see
+masr/model_utils/conformer/{model,encoder,attention,convolution,subsampling}.py), so the
+very same dict can be fed to ``reference_model.load_state_dict`` (to make golden vectors in the
+build container) and to :class:`masr_b200.engine.Engine` (on the GPU box).
+
+Nothing in here depends on the reference tree or on the oracle.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from typing import Dict, List
+
+import numpy as np
+
+DEFAULT_VOCAB_SIZE = 4233  # WeNet AISHELL-1 unit count; a free parameter, reported with every number
+
+
+def _uniform(rng, shape, bound):
+    return rng.uniform(-bound, bound, size=shape).astype(np.float32)
+
+
+def _linear(rng, sd, name, out_f, in_f, bias=True, gain=1.0):
+    b = gain / math.sqrt(in_f)
+    sd[name + ".weight"] = _uniform(rng, (out_f, in_f), b)
+    if bias:
+        sd[name + ".bias"] = _uniform(rng, (out_f,), b)
+
+
+def _layer_norm(rng, sd, name, dim):
+    # non-trivial affine parameters so a kernel that drops gamma/beta cannot pass
+    sd[name + ".weight"] = (1.0 + 0.1 * rng.standard_normal(dim)).astype(np.float32)
+    sd[name + ".bias"] = (0.1 * rng.standard_normal(dim)).astype(np.float32)
+
+
+def cmvn_stats(seed: int = 0, dim: int = 80):
+    """Synthetic global CMVN constants in the value range of real log-mel features
+    (fbank of sigma=0.1 noise has mean ~20.6, std ~3.1 — SURVEY.md §8d)."""
+    rng = np.random.default_rng(1000 + seed)
+    mean = (20.6 + 1.5 * rng.standard_normal(dim)).astype(np.float32)
+    istd = (1.0 / (3.1 * (1.0 + 0.1 * rng.uniform(-1, 1, dim)))).astype(np.float32)
+    return mean, istd
+
+
+def conformer_state_dict(seed: int = 0,
+                         vocab_size: int = DEFAULT_VOCAB_SIZE,
+                         input_dim: int = 80,
+                         output_size: int = 256,
+                         attention_heads: int = 4,
+                         linear_units: int = 2048,
+                         num_blocks: int = 12,
+                         cnn_module_kernel: int = 15,
+                         ctc_gain: float = 6.0,
+                         blank_bias: float = 12.3) -> Dict[str, np.ndarray]:
+    """Encoder + CTC-head tensors of a Conformer in the reference layout.
+
+    ``ctc_gain`` sharpens the CTC posterior and ``blank_bias`` lifts the blank logit so the
+    greedy path contains blanks and repeats (default-init posteriors are flat and never
+    blank — SURVEY.md §7 "hard parts").  The attention *decoder* of the reference model
+    (166 tensors) is not on the inference path and is not generated.
+    """
+    rng = np.random.default_rng(seed)
+    d, h = output_size, attention_heads
+    dk = d // h
+    sd: Dict[str, np.ndarray] = {}
+    mean, istd = cmvn_stats(seed, input_dim)
+    sd["encoder.global_cmvn.mean"] = mean
+    sd["encoder.global_cmvn.istd"] = istd
+    # Conv2dSubsampling4 (conformer/subsampling.py:65-91)
+    sd["encoder.embed.conv.0.weight"] = _uniform(rng, (d, 1, 3, 3), 1.0 / 3.0)
+    sd["encoder.embed.conv.0.bias"] = _uniform(rng, (d,), 1.0 / 3.0)
+    b2 = 1.0 / math.sqrt(d * 9)
+    sd["encoder.embed.conv.2.weight"] = _uniform(rng, (d, d, 3, 3), b2)
+    sd["encoder.embed.conv.2.bias"] = _uniform(rng, (d,), b2)
+    f2 = ((input_dim - 1) // 2 - 1) // 2
+    _linear(rng, sd, "encoder.embed.out.0", d, d * f2)
+    for i in range(num_blocks):
+        p = f"encoder.encoders.{i}."
+        xav = math.sqrt(6.0 / (h + dk))
+        sd[p + "self_attn.pos_bias_u"] = _uniform(rng, (h, dk), xav)
+        sd[p + "self_attn.pos_bias_v"] = _uniform(rng, (h, dk), xav)
+        for nm in ("linear_q", "linear_k", "linear_v", "linear_out"):
+            _linear(rng, sd, p + "self_attn." + nm, d, d)
+        _linear(rng, sd, p + "self_attn.linear_pos", d, d, bias=False)
+        for ff in ("feed_forward", "feed_forward_macaron"):
+            _linear(rng, sd, p + ff + ".w_1", linear_units, d)
+            _linear(rng, sd, p + ff + ".w_2", d, linear_units)
+        bpw = 1.0 / math.sqrt(d)
+        sd[p + "conv_module.pointwise_conv1.weight"] = _uniform(rng, (2 * d, d, 1), bpw)
+        sd[p + "conv_module.pointwise_conv1.bias"] = _uniform(rng, (2 * d,), bpw)
+        bdw = 1.0 / math.sqrt(cnn_module_kernel)
+        sd[p + "conv_module.depthwise_conv.weight"] = _uniform(rng, (d, 1, cnn_module_kernel), bdw)
+        sd[p + "conv_module.depthwise_conv.bias"] = _uniform(rng, (d,), bdw)
+        _layer_norm(rng, sd, p + "conv_module.norm", d)
+        sd[p + "conv_module.pointwise_conv2.weight"] = _uniform(rng, (d, d, 1), bpw)
+        sd[p + "conv_module.pointwise_conv2.bias"] = _uniform(rng, (d,), bpw)
+        for nm in ("norm_ff", "norm_mha", "norm_ff_macaron", "norm_conv", "norm_final"):
+            _layer_norm(rng, sd, p + nm, d)
+    _layer_norm(rng, sd, "encoder.after_norm", d)
+    _linear(rng, sd, "ctc.ctc_lo", vocab_size, d, gain=ctc_gain)
+    sd["ctc.ctc_lo.bias"][0] += np.float32(blank_bias)
+    return sd
+
+
+def vocabulary(vocab_size: int = DEFAULT_VOCAB_SIZE) -> List[str]:
+    """``<blank>``, ``<unk>``, CJK code points…, one ``<space>``, ``<eos>`` last — the order
+    the reference's ``create_data`` writes (masr/trainer.py:480-488)."""
+    toks = ["<blank>", "<unk>"]
+    n_mid = vocab_size - 3
+    toks += [chr(0x4E00 + i) for i in range(n_mid - 1)]
+    toks += ["<space>"]
+    toks += ["<eos>"]
+    assert len(toks) == vocab_size
+    return toks
+
+
+def write_vocabulary(path: str, vocab_size: int = DEFAULT_VOCAB_SIZE):
+    """One ``token\\tcount`` per line, line index == id (text_featurizer.py:52-59)."""
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "w", encoding="utf-8") as f:
+        for i, t in enumerate(vocabulary(vocab_size)):
+            f.write(f"{t}\t{max(1, vocab_size - i)}\n")
+
+
+def write_mean_istd(path: str, seed: int = 0, dim: int = 80):
+    """``{"mean": [...], "istd": [...], "feature_method": ...}`` (normalizer.py:88-92)."""
+    mean, istd = cmvn_stats(seed, dim)
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump({"mean": [float(v) for v in mean], "istd": [float(v) for v in istd],
+                   "feature_method": "fbank"}, f)
+
+
+def noise_audio(seed: int, num_samples: int, sigma: float = 0.1) -> np.ndarray:
+    """BASELINE.md §5 synthetic input: ``0.1 * standard_normal`` float32 (RMS ~ -20 dB)."""
+    rng = np.random.default_rng(seed)
+    return (sigma * rng.standard_normal(num_samples)).astype(np.float32)
+
+
+def speechlike_audio(seed: int, num_samples: int, sample_rate: int = 16000) -> np.ndarray:
+    """A non-stationary test signal: gliding harmonics under a syllable-rate envelope plus a
+    noise floor, so successive encoder frames differ and the greedy path varies."""
+    rng = np.random.default_rng(7000 + seed)
+    t = np.arange(num_samples, dtype=np.float64) / sample_rate
+    f0 = 110.0 + 60.0 * np.sin(2 * np.pi * 0.7 * t + rng.uniform(0, 6.28))
+    phase = 2 * np.pi * np.cumsum(f0) / sample_rate
+    sig = np.zeros(num_samples)
+    for k in range(1, 12):
+        fk = rng.uniform(0.3, 1.0) / k
+        sig += fk * np.sin(k * phase + rng.uniform(0, 6.28)) * (0.6 + 0.4 * np.sin(2 * np.pi * rng.uniform(0.5, 3.0) * t))
+    env = 0.5 * (1 + np.sin(2 * np.pi * rng.uniform(2.5, 4.5) * t + rng.uniform(0, 6.28)))
+    env = env ** 2
+    sig = sig * env * 0.08 + 0.004 * rng.standard_normal(num_samples)
+    return sig.astype(np.float32)
+
+
+def to_torch(sd: Dict[str, np.ndarray]):
+    import torch
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}

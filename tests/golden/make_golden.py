@@ -1,0 +1,162 @@
+"""Generate the golden vectors in this directory by running the UNMODIFIED reference
+(/root/reference, yeyupiaoling/MASR @ fe0010de) in the build container through
+``oracle/ref_shims.py``.  The reference has no tests or golden vectors of its own,
+and it cannot travel to the GPU box, so its outputs on deterministic synthetic inputs are frozen here.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz / *.json
+
+Inputs are regenerated from seeds by ``masr_b200.synth`` (weights, vocabulary, CMVN, audio), so only
+the reference's OUTPUTS are stored.
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+from oracle import ref_shims  # noqa: E402
+
+ref_shims.install()
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+from masr_b200 import synth  # noqa: E402
+
+V = synth.DEFAULT_VOCAB_SIZE
+
+# (name, kind, seed, num_samples[, scale])
+FBANK_CASES = [
+    ("noise_1s", "noise", 0, 16000),
+    ("speech_0p7s", "speech", 1, 11200),
+    ("speech_min", "speech", 2, 400),          # exactly one frame
+    ("speech_loud", "speech", 3, 8000, 30.0),  # clips at int16 after normalisation? (exercises the clamp path)
+    ("speech_quiet", "speech", 4, 8000, 1e-3),
+]
+
+ENCODER_CASES = [  # (name, streaming, weight seed, audio kind, audio seed, samples)
+    ("causal_speech_1p5s", True, 0, "speech", 10, 24000),
+    ("causal_noise_1s", True, 0, "noise", 11, 16000),
+    ("noncausal_speech_1p2s", False, 1, "speech", 12, 19200),
+]
+
+STREAM_CASE = ("stream_speech_3p4s", 0, "speech", 30, 54400, 8000)  # weight seed, kind, audio seed, samples, push
+
+
+def make_audio(kind, seed, n, scale=1.0):
+    x = synth.noise_audio(seed, n) if kind == "noise" else synth.speechlike_audio(seed, n)
+    return (x * np.float32(scale)).astype(np.float32)
+
+
+def build_reference_model(tmp, streaming, wseed):
+    from masr.model_utils.conformer.model import ConformerModel
+    cfg = yaml.safe_load(open(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "conformer.yml"), encoding="utf-8"))
+    mi = os.path.join(tmp, f"mean_istd_{wseed}.json")
+    synth.write_mean_istd(mi, wseed)
+    model = ConformerModel(input_dim=80, vocab_size=V, mean_istd_path=mi, streaming=streaming,
+                           encoder_conf=cfg["encoder_conf"], decoder_conf=cfg["decoder_conf"], **cfg["model_conf"])
+    sd = synth.to_torch(synth.conformer_state_dict(wseed, V))
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith("decoder.") for k in res.missing_keys)
+    return model.eval(), cfg, mi
+
+
+def gen_fbank():
+    from masr.data_utils.audio import AudioSegment
+    from masr.data_utils.featurizer.audio_featurizer import AudioFeaturizer
+    af = AudioFeaturizer(feature_method="fbank", n_mels=80, sample_rate=16000, use_dB_normalization=True, target_dB=-20)
+    out = {}
+    meta = []
+    for case in FBANK_CASES:
+        name, kind, seed, n = case[:4]
+        scale = case[4] if len(case) > 4 else 1.0
+        x = make_audio(kind, seed, n, scale)
+        seg = AudioSegment.from_ndarray(x.copy(), 16000)
+        feat = af.featurize(seg)                 # normalises seg in place
+        q = seg.to("int16")
+        out[name + "/feat"] = np.asarray(feat, np.float32)
+        out[name + "/int16"] = q
+        meta.append({"name": name, "kind": kind, "seed": seed, "samples": n, "scale": scale})
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "fbank_golden.npz"), **out)
+    print("fbank_golden.npz", {k: v.shape for k, v in out.items() if k != "meta"})
+
+
+def gen_encoder(tmp):
+    from masr.data_utils.audio import AudioSegment
+    from masr.data_utils.featurizer.audio_featurizer import AudioFeaturizer
+    from masr.decoders.ctc_greedy_decoder import greedy_decoder
+    af = AudioFeaturizer(feature_method="fbank", n_mels=80, sample_rate=16000, use_dB_normalization=True, target_dB=-20)
+    vocab = synth.vocabulary(V)
+    out, meta = {}, []
+    for name, streaming, wseed, kind, aseed, n in ENCODER_CASES:
+        model, _, _ = build_reference_model(tmp, streaming, wseed)
+        scripted = model.export()                # TorchScript, as MASRTrainer.export does (trainer.py:684)
+        x = make_audio(kind, aseed, n)
+        feat = torch.from_numpy(af.featurize(AudioSegment.from_ndarray(x.copy(), 16000)))[None]
+        with torch.no_grad():
+            probs = scripted.get_encoder_out(feat, torch.tensor([feat.shape[1]]))[0]
+            enc, _ = model.encoder(feat, torch.tensor([feat.shape[1]]), decoding_chunk_size=-1, num_decoding_left_chunks=-1)
+        score, text = greedy_decoder(probs.numpy(), vocab)
+        top = probs.topk(8, dim=1)
+        out[name + "/feat"] = feat[0].numpy()
+        out[name + "/enc"] = enc[0].numpy()
+        out[name + "/top_p"] = top.values.numpy()
+        out[name + "/top_i"] = top.indices.numpy().astype(np.int32)
+        out[name + "/ids"] = probs.argmax(1).numpy().astype(np.int32)
+        meta.append({"name": name, "streaming": streaming, "wseed": wseed, "kind": kind, "aseed": aseed, "samples": n,
+                     "score": score, "text": text})
+        print(name, "T", probs.shape[0], "score", score, "text", text)
+    out["meta"] = np.frombuffer(json.dumps(meta, ensure_ascii=False).encode("utf-8"), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "conformer_golden.npz"), **out)
+
+
+def gen_predictor(tmp):
+    """The real ``MASRPredictor`` end to end (greedy): whole-utterance and streaming pushes."""
+    from masr.predict import MASRPredictor
+    name, wseed, kind, aseed, n, push = STREAM_CASE
+    model, cfg, mi = build_reference_model(tmp, True, wseed)
+    mp = os.path.join(tmp, "inference.pt")
+    torch.jit.save(model.export(), mp)
+    vp = os.path.join(tmp, "vocabulary.txt")
+    synth.write_vocabulary(vp, V)
+    cfg["dataset_conf"]["dataset_vocab"] = vp
+    cfg["dataset_conf"]["mean_istd_path"] = mi
+    cfg["decoder"] = "ctc_greedy"
+    np.random.seed(0)
+    pred = MASRPredictor(configs=cfg, model_path=mp, use_gpu=False)
+    x = make_audio(kind, aseed, n)
+    whole = pred.predict(audio_data=x.copy())
+    pcm = (np.clip(x, -1, 1) * 32767).astype("<i2")
+    pushes = []
+    pred.reset_stream()
+    for s in range(0, len(pcm), push):
+        chunk = pcm[s:s + push].tobytes()
+        is_end = s + push >= len(pcm)
+        r = pred.predict_stream(audio_data=chunk, is_end=is_end)
+        pushes.append(None if r is None else {"text": r["text"], "score": r["score"]})
+    pred.reset_stream()
+    # second run with float ndarray pushes, to pin reset_stream + the ndarray path
+    pushes_nd = []
+    for s in range(0, len(x), push):
+        r = pred.predict_stream(audio_data=x[s:s + push].copy(), is_end=s + push >= len(x))
+        pushes_nd.append(None if r is None else {"text": r["text"], "score": r["score"]})
+    data = {"name": name, "wseed": wseed, "kind": kind, "aseed": aseed, "samples": n, "push": push,
+            "whole": whole, "pushes_pcm": pushes, "pushes_ndarray": pushes_nd}
+    with open(os.path.join(HERE, "predictor_golden.json"), "w", encoding="utf-8") as f:
+        json.dump(data, f, ensure_ascii=False, indent=1)
+    print("predictor whole", whole)
+    print("pushes", pushes)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    with tempfile.TemporaryDirectory() as tmp:
+        gen_fbank()
+        gen_encoder(tmp)
+        gen_predictor(tmp)

@@ -1,0 +1,65 @@
+"""CPU, build container only: the oracle against the live, unmodified reference (skipped where
+/root/reference is absent, e.g. on the GPU box)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_audio, synth_weights
+from masr_b200 import synth
+from oracle import conformer as oc, fbank as ob, ref_shims
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not present")]
+
+
+@pytest.fixture(scope="module")
+def ref_model(tmp_path_factory):
+    ref_shims.install()
+    import yaml
+    from masr.model_utils.conformer.model import ConformerModel
+    tmp = tmp_path_factory.mktemp("ref")
+    cfg = yaml.safe_load(open(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "conformer.yml"), encoding="utf-8"))
+    mi = str(tmp / "mi.json")
+    synth.write_mean_istd(mi, 0)
+    m = ConformerModel(input_dim=80, vocab_size=synth.DEFAULT_VOCAB_SIZE, mean_istd_path=mi, streaming=True,
+                       encoder_conf=cfg["encoder_conf"], decoder_conf=cfg["decoder_conf"], **cfg["model_conf"]).eval()
+    m.load_state_dict(synth.to_torch(synth_weights(0)), strict=False)
+    return m
+
+
+def test_featurizer_matches(ref_model):
+    from masr.data_utils.audio import AudioSegment
+    from masr.data_utils.featurizer.audio_featurizer import AudioFeaturizer
+    af = AudioFeaturizer(feature_method="fbank", n_mels=80, sample_rate=16000, use_dB_normalization=True, target_dB=-20)
+    for kind, seed, n in [("noise", 5, 20000), ("speech", 6, 33333)]:
+        x = make_audio(kind, seed, n)
+        ref = af.featurize(AudioSegment.from_ndarray(x.copy(), 16000))
+        assert np.abs(ob.featurize(x.copy()) - ref).max() < 5e-4
+    pcm = (make_audio("speech", 7, 8000) * 20000).astype(np.int16)
+    ref = af.featurize(AudioSegment.from_pcm_bytes(pcm.tobytes()))
+    assert np.abs(ob.featurize(ob.pcm_bytes_to_float32(pcm.tobytes())) - ref).max() < 5e-4
+
+
+def test_full_and_chunk_forward_match(ref_model):
+    sd = synth.to_torch(synth_weights(0))
+    cfg = oc.ConformerConfig()
+    feat = torch.from_numpy(ob.featurize(make_audio("speech", 8, 16000 * 3)))[None]
+    with torch.no_grad():
+        ref = ref_model.get_encoder_out(feat, torch.tensor([feat.shape[1]]))
+        got = oc.get_encoder_out(sd, cfg, feat)
+        assert (ref - got).abs().max().item() < 1e-6
+        st = oc.ChunkState()
+        att = torch.zeros(0, 0, 0, 0)
+        cnn = torch.zeros(0, 0, 0, 0)
+        off = 0
+        for cur in range(0, feat.shape[1] - 67 + 1, 64):
+            ch = feat[:, cur:cur + 67]
+            pr, att, cnn = ref_model.get_encoder_out_chunk(ch, off, -16, att, cnn)
+            off += pr.shape[1]
+            pm = oc.get_encoder_out_chunk(sd, cfg, ch, st, -16)
+            assert (pr - pm).abs().max().item() < 1e-6
+            assert (att - st.att_cache).abs().max().item() < 1e-6
+            assert (cnn - st.cnn_cache).abs().max().item() < 1e-6
