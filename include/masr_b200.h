@@ -95,26 +95,53 @@ int masr_gemm_f32(const float* A, int64_t lda, const float* W, const float* bias
                   int64_t ldr, float* C, int64_t ldc, int M, int N, int K, int epilogue, float alpha,
                   void* stream);
 
+/* Tensor-core (tcgen05/TMEM/TMA) variant of masr_gemm_f32 with fp32-grade results: operands are fp16
+ * (h, l) pairs, h = fp16(x), l = fp16((x - h) * 2^11) (masr_split_f16); C ~= Ah.Wh^T + 2^-11 (Ah.Wl^T + Al.Wh^T)
+ * accumulated in fp32.  Output: fp32 C and/or the (Ch, Cl) pair the next GEMM consumes (either may be NULL,
+ * not both).  K % 64 == 0, lda % 8 == 0, ldc % 8 == 0 (ldc % 4 when only fp32 is written); W is [N, K] dense. */
+int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl,
+                       const float* bias, const float* residual, int64_t ldr, float* C, void* Ch, void* Cl,
+                       int64_t ldc, int M, int N, int K, int epilogue, float alpha, void* stream);
+
+/* Conv2dSubsampling4's first conv (as masr_conv1_cmvn_relu_f32) written as fp16 (h,l) pairs in four
+ * (t,f)-parity planes [4][B][(F1max+1)/2][20][C], and its second conv + ReLU (subsampling.py:83-84) as a
+ * tensor-core implicit GEMM over those planes: the stride-2 window of tap (kh,kw) is a dense TMA box of plane
+ * (kh&1, kw&1).  Wh/Wl: split of the [C, 3,3,C]-permuted weight.  Output rows ((b*T2 + t)*19 + f) x C. */
+int masr_conv1_cmvn_relu_planes_f16(const float* feats, const float* mean, const float* istd, const float* w1,
+                                    const float* b1, void* planes_h, void* planes_l, int B, int Fmax, int idim,
+                                    int F1max, int W1, int C, void* stream);
+int masr_conv2_tc_f16x2(const void* c1h, const void* c1l, const void* Wh, const void* Wl, const float* bias,
+                        float* out, void* outh, void* outl, int B, int F1, int T2, int C, void* stream);
+
+/* fp32 -> fp16 (h, l) pair, elementwise over n contiguous values. */
+int masr_split_f16(const float* x, void* h, void* l, int64_t n, void* stream);
+
 /* torch.nn.LayerNorm(D, eps) over the last dimension (encoder.py:64-72; convolution.py:66). */
 int masr_layernorm_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* y, int64_t ldy,
                        int M, int D, float eps, void* stream);
 
+/* LayerNorm writing the fp16 (h, l) operand pair of masr_gemm_tc_f16x2 instead of fp32. */
+int masr_layernorm_split_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, void* yh, void* yl,
+                             int64_t ldy, int M, int D, float eps, void* stream);
+
 /* RelPositionMultiHeadedAttention core (masr/model_utils/conformer/attention.py:230-251,107-118):
  * Q rows (b*q_bstride + i), K/V rows (b*k_bstride + j), head h at column h*d_k; P [>=max klen, ldp] =
  * linear_pos(pos_emb) rows aligned with key index j; pos_u/pos_v [H,d_k]; O like Q.
- * q_lens/k_lens int32[B]: valid queries / keys per utterance (rows beyond q_lens are written as 0). */
+ * q_lens/k_lens int32[B]: valid queries / keys per utterance (rows beyond q_lens are written as 0).
+ * Output: fp32 O and/or the fp16 (Oh, Ol) operand pair of masr_gemm_tc_f16x2 (same ldo; either may be NULL). */
 int masr_relpos_attention_f32(const float* Q, int64_t ldq, int64_t q_bstride, const float* K, const float* V,
                               int64_t ldk, int64_t k_bstride, const float* P, int64_t ldp, const float* pos_u,
-                              const float* pos_v, float* O, int64_t ldo, int64_t o_bstride, const int* q_lens,
-                              const int* k_lens, int B, int H, int d_k, int max_q, void* stream);
+                              const float* pos_v, float* O, void* Oh, void* Ol, int64_t ldo, int64_t o_bstride,
+                              const int* q_lens, const int* k_lens, int B, int H, int d_k, int max_q, void* stream);
 
 /* ConvolutionModule middle (masr/model_utils/conformer/convolution.py:121-126): depthwise Conv1d(k)
  * -> LayerNorm(C) -> SiLU.  y[b,t,:] for t < out_rows from g[b, t - lpad + k, :], k < kernel_size;
- * g rows < 0 read pad_vec (NULL = 0), rows >= in_lens[b] read 0.  w [C,k] (reference [C,1,k]). */
+ * g rows < 0 read pad_vec (NULL = 0), rows >= in_lens[b] read 0.  w [C,k] (reference [C,1,k]).
+ * Output: fp32 y and/or the fp16 (yh, yl) pair (either may be NULL). */
 int masr_dwconv_ln_silu_f32(const float* g, int64_t ldg, int64_t g_bstride, const float* w, const float* bias,
-                            const float* ln_gamma, const float* ln_beta, const float* pad_vec, float* y,
-                            int64_t ldy, int64_t y_bstride, const int* in_lens, int B, int C, int kernel_size,
-                            int lpad, int out_rows, float eps, void* stream);
+                            const float* ln_gamma, const float* ln_beta, const float* pad_vec, float* y, void* yh,
+                            void* yl, int64_t ldy, int64_t y_bstride, const int* in_lens, int B, int C,
+                            int kernel_size, int lpad, int out_rows, float eps, void* stream);
 
 /* ---- CTC head / greedy decode ------------------------------------------------------------------- */
 

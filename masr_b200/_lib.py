@@ -28,10 +28,15 @@ SIGNATURES = {
     "masr_conv1_cmvn_relu_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "masr_conv2_s2_relu_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "masr_gemm_f32": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _vp],
+    "masr_gemm_tc_f16x2": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _f, _vp],
+    "masr_split_f16": [_vp, _vp, _vp, _i64, _vp],
+    "masr_conv1_cmvn_relu_planes_f16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "masr_conv2_tc_f16x2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "masr_layernorm_f32": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
-    "masr_relpos_attention_f32": [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64,
+    "masr_layernorm_split_f16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
+    "masr_relpos_attention_f32": [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                   _vp, _vp, _i, _i, _i, _i, _vp],
-    "masr_dwconv_ln_silu_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i,
+    "masr_dwconv_ln_silu_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i,
                                 _i, _f, _vp],
     "masr_ctc_frame_argmax_f32": [_vp, _i64, _i, _i, _vp, _vp, _vp, _i64, _vp],
     "masr_ctc_greedy_collapse": [_vp, _vp, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp],

@@ -10,6 +10,7 @@
 // each row of a ragged batch is computed exactly as if it were alone (the B=1 API semantics).
 //
 // One CTA per (64-query tile, head, utterance); 64-key tiles stream through shared memory.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -24,7 +25,7 @@ struct AttnParams {
     const float* K; const float* V; int64_t ldk, k_bstride;
     const float* P; int64_t ldp;
     const float* pos_u; const float* pos_v;
-    float* O; int64_t ldo, o_bstride;
+    float* O; __half* Oh; __half* Ol; int64_t ldo, o_bstride;
     const int* q_lens; const int* k_lens;
     float scale;
     int max_q;
@@ -59,13 +60,19 @@ __global__ void __launch_bounds__(256) relpos_attention_kernel(AttnParams p) {
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
     const int qlen = p.q_lens[b], klen = p.k_lens[b];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    float* obase = p.O + ((int64_t)b * p.o_bstride + q0) * p.ldo + h * AD;
+    const int64_t ooff = ((int64_t)b * p.o_bstride + q0) * p.ldo + h * AD;
+    float* obase = p.O ? p.O + ooff : nullptr;
     if (q0 >= qlen || klen <= 0) {
         // padded query tile: deterministic zeros (rows are never read for valid output)
         for (int idx = tid; idx < AQ * 16; idx += 256) {
             int r = idx >> 4, c = (idx & 15) * 4;
-            if (q0 + r < p.max_q)
-                *reinterpret_cast<float4*>(obase + (int64_t)r * p.ldo + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q0 + r < p.max_q) {
+                if (obase) *reinterpret_cast<float4*>(obase + (int64_t)r * p.ldo + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.Oh) {
+                    *reinterpret_cast<uint2*>(p.Oh + ooff + (int64_t)r * p.ldo + c) = make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2*>(p.Ol + ooff + (int64_t)r * p.ldo + c) = make_uint2(0u, 0u);
+                }
+            }
         }
         return;
     }
@@ -171,7 +178,20 @@ __global__ void __launch_bounds__(256) relpos_attention_kernel(AttnParams p) {
             const float inv = 1.0f / row_l[r];
             out = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
         }
-        if (q0 + r < p.max_q) *reinterpret_cast<float4*>(obase + (int64_t)r * p.ldo + tx * 4) = out;
+        if (q0 + r < p.max_q) {
+            if (obase) *reinterpret_cast<float4*>(obase + (int64_t)r * p.ldo + tx * 4) = out;
+            if (p.Oh) {
+                const float ov[4] = {out.x, out.y, out.z, out.w};
+                __half hh[4], ll[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hh[j] = __float2half_rn(ov[j]);
+                    ll[j] = __float2half_rn((ov[j] - __half2float(hh[j])) * 2048.0f);
+                }
+                *reinterpret_cast<uint2*>(p.Oh + ooff + (int64_t)r * p.ldo + tx * 4) = *reinterpret_cast<const uint2*>(hh);
+                *reinterpret_cast<uint2*>(p.Ol + ooff + (int64_t)r * p.ldo + tx * 4) = *reinterpret_cast<const uint2*>(ll);
+            }
+        }
     }
 }
 
@@ -183,11 +203,11 @@ using namespace masr;
 
 extern "C" int masr_relpos_attention_f32(const float* Q, int64_t ldq, int64_t q_bstride, const float* K,
                                          const float* V, int64_t ldk, int64_t k_bstride, const float* P, int64_t ldp,
-                                         const float* pos_u, const float* pos_v, float* O, int64_t ldo,
-                                         int64_t o_bstride, const int* q_lens, const int* k_lens, int B, int H,
-                                         int d_k, int max_q, void* stream) {
+                                         const float* pos_u, const float* pos_v, float* O, void* Oh, void* Ol,
+                                         int64_t ldo, int64_t o_bstride, const int* q_lens, const int* k_lens, int B,
+                                         int H, int d_k, int max_q, void* stream) {
     if (B == 0 || max_q == 0) return MASR_OK;
-    MASR_REQUIRE(Q && K && V && P && pos_u && pos_v && O && q_lens && k_lens, "masr_relpos_attention_f32: null pointer");
+    MASR_REQUIRE(Q && K && V && P && pos_u && pos_v && (O || (Oh && Ol)) && q_lens && k_lens, "masr_relpos_attention_f32: null pointer");
     MASR_REQUIRE(d_k == AD, "masr_relpos_attention_f32: d_k=%d unsupported (this build: 64)", d_k);
     MASR_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0,
                  "masr_relpos_attention_f32: leading dimensions must be multiples of 4");
@@ -201,7 +221,7 @@ extern "C" int masr_relpos_attention_f32(const float* Q, int64_t ldq, int64_t q_
         if (e != cudaSuccess) { set_last_error("attention smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set[dev] = true;
     }
-    AttnParams p{Q, ldq, q_bstride, K, V, ldk, k_bstride, P, ldp, pos_u, pos_v, O, ldo, o_bstride, q_lens, k_lens,
+    AttnParams p{Q, ldq, q_bstride, K, V, ldk, k_bstride, P, ldp, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, ldo, o_bstride, q_lens, k_lens,
                  1.0f / sqrtf((float)d_k), max_q};
     dim3 grid((max_q + AQ - 1) / AQ, H, B);
     relpos_attention_kernel<<<grid, 256, kAttnSmem, (cudaStream_t)stream>>>(p);

@@ -10,6 +10,8 @@
 //   * streaming chunk: the caller runs pointwise_conv1 over [cache ++ chunk] and calls with lpad=0.
 //
 // HBM-bound: 4*(1 + 1) bytes per element, (TT+K-1)/TT read amplification served by L1/L2.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace masr {
@@ -21,7 +23,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const float* __rest
                                                              const float* __restrict__ ln_g,
                                                              const float* __restrict__ ln_b,
                                                              const float* __restrict__ pad_vec, float* __restrict__ y,
-                                                             int64_t ldy, int64_t y_bstride,
+                                                             __half* __restrict__ yh, __half* __restrict__ yl, int64_t ldy, int64_t y_bstride,
                                                              const int* __restrict__ in_lens, int lpad, int out_rows,
                                                              float eps) {
     constexpr int C = 256;
@@ -80,11 +82,19 @@ __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const float* __rest
     }
     __syncthreads();
     const float gg = __ldg(ln_g + c), bb = __ldg(ln_b + c);
-    float* yb = y + (int64_t)b * y_bstride * ldy + c;
+    const int64_t yoff = (int64_t)b * y_bstride * ldy + c;
 #pragma unroll
     for (int j = 0; j < TT; ++j) {
         const int t = t0 + j;
-        if (t < out_rows) yb[(int64_t)t * ldy] = silu_f(dev[j] * stat[j] * gg + bb);
+        if (t < out_rows) {
+            const float o = silu_f(dev[j] * stat[j] * gg + bb);
+            if (y) y[yoff + (int64_t)t * ldy] = o;
+            if (yh) {
+                const __half hh = __float2half_rn(o);
+                yh[yoff + (int64_t)t * ldy] = hh;
+                yl[yoff + (int64_t)t * ldy] = __float2half_rn((o - __half2float(hh)) * 2048.0f);
+            }
+        }
     }
 }
 
@@ -94,18 +104,18 @@ using namespace masr;
 
 extern "C" int masr_dwconv_ln_silu_f32(const float* g, int64_t ldg, int64_t g_bstride, const float* w,
                                        const float* bias, const float* ln_gamma, const float* ln_beta,
-                                       const float* pad_vec, float* y, int64_t ldy, int64_t y_bstride,
+                                       const float* pad_vec, float* y, void* yh, void* yl, int64_t ldy, int64_t y_bstride,
                                        const int* in_lens, int B, int C, int kernel_size, int lpad, int out_rows,
                                        float eps, void* stream) {
     if (B == 0 || out_rows == 0) return MASR_OK;
-    MASR_REQUIRE(g && w && bias && ln_gamma && ln_beta && y && in_lens, "masr_dwconv_ln_silu_f32: null pointer");
+    MASR_REQUIRE(g && w && bias && ln_gamma && ln_beta && (y || (yh && yl)) && in_lens, "masr_dwconv_ln_silu_f32: null pointer");
     MASR_REQUIRE(C == 256, "masr_dwconv_ln_silu_f32: C=%d unsupported (this build: 256)", C);
     constexpr int TT = 8;
     dim3 grid((out_rows + TT - 1) / TT, B);
     cudaStream_t st = (cudaStream_t)stream;
 #define MASR_DW_LAUNCH(KS)                                                                                       \
     dwconv_ln_silu_kernel<KS, TT><<<grid, 256, 0, st>>>(g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
-                                                        ldy, y_bstride, in_lens, lpad, out_rows, eps)
+                                                        (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps)
     switch (kernel_size) {
         case 7: MASR_DW_LAUNCH(7); break;
         case 15: MASR_DW_LAUNCH(15); break;

@@ -50,7 +50,14 @@ class GreedyResult:
 class ConformerEngine:
     """Conformer (configs/conformer.yml) inference on one B200."""
 
-    def __init__(self, weights_src, streaming: bool = True, device: str = "cuda", max_len: int = 5000):
+    def __init__(self, weights_src, streaming: bool = True, device: str = "cuda", max_len: int = 5000,
+                 gemm: str = "tc"):
+        """``gemm``: "tc" = tcgen05 FP16x2-split tensor-core GEMMs (fp32-grade results, csrc/tc_gemm.cu) for the
+        batched path; "simt" = the fp32 FMA-pipe GEMMs (csrc/gemm.cu).  The single-stream chunk path always uses
+        the fp32 kernels (16-row problems are launch-bound, not math-bound)."""
+        if gemm not in ("tc", "simt"):
+            raise ValueError("gemm must be 'tc' or 'simt'")
+        self.gemm_path = gemm
         if not torch.cuda.is_available():
             raise _lib.MasrB200Error("masr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -71,21 +78,94 @@ class ConformerEngine:
         self.w1_cols = (self.w.idim - 1) // 2
         self._ws: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self.launches = 0
+        self._pinned: Optional[torch.Tensor] = None      # grow-only pinned staging buffer for H2D copies
+        self._staged: Optional[torch.cuda.Event] = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self.last_gain = None
+        self.prof: Optional[Dict[str, list]] = None      # tag -> [(start_event, end_event)], see profile()
         self._precompute_pos()
+        self._tcw = {}
+        if self.gemm_path == "tc":
+            self._split_weights()
+
+    # ---- tensor-core path helpers ---------------------------------------------------------------
+    def _split(self, x: torch.Tensor):
+        """fp32 tensor -> fp16 (h, l) pair (masr_split_f16)."""
+        x = x.contiguous()
+        h = torch.empty(x.shape, dtype=torch.float16, device=self.device)
+        l = torch.empty(x.shape, dtype=torch.float16, device=self.device)
+        call("masr_split_f16", _p(x), _p(h), _p(l), x.numel(), self._stream())
+        return h, l
+
+    def _split_weights(self):
+        w = self.w
+        t = self._tcw
+        t["conv2"] = self._split(w.conv2_w)
+        t["embed"] = self._split(w.embed_w)
+        t["ctc"] = self._split(w.ctc_w)
+        for i, L in enumerate(w.layers):
+            t[i, "ffm1"] = self._split(L.ffm[0]); t[i, "ffm2"] = self._split(L.ffm[2])
+            t[i, "qkv"] = self._split(L.wqkv); t[i, "wo"] = self._split(L.wo)
+            t[i, "pw1"] = self._split(L.pw1); t[i, "pw2"] = self._split(L.pw2)
+            t[i, "ff1"] = self._split(L.ff[0]); t[i, "ff2"] = self._split(L.ff[2])
+        torch.cuda.synchronize(self.device)
+
+    def _tc(self, A, lda, W, bias, M, N, K, epi=EPI_BIAS, alpha=1.0, residual=None, ldr=0, C=None, Cp=None, ldc=0,
+            tag="gemm"):
+        """C / (Ch,Cl) = epi(A.W^T): A, W fp16 (h,l) pairs."""
+        self._k(tag, "masr_gemm_tc_f16x2", _p(A[0]), _p(A[1]), lda, _p(W[0]), _p(W[1]), _p(bias), _p(residual), ldr,
+                _p(C), None if Cp is None else _p(Cp[0]), None if Cp is None else _p(Cp[1]), ldc, M, N, K, epi, alpha)
+
+    def _ln_split(self, x, gb, yp, M):
+        self._k("layernorm", "masr_layernorm_split_f16", _p(x), self.d, _p(gb[0]), _p(gb[1]), _p(yp[0]), _p(yp[1]),
+                self.d, M, self.d, 1e-5)
 
     # ------------------------------------------------------------------------------------------
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _gemm(self, A, lda, W, bias, C, ldc, M, N, K, epi=EPI_BIAS, alpha=1.0, residual=None, ldr=0):
+    def _gemm(self, A, lda, W, bias, C, ldc, M, N, K, epi=EPI_BIAS, alpha=1.0, residual=None, ldr=0, tag="gemm"):
+        ev = self._prof_begin(tag)
         call("masr_gemm_f32", _p(A), lda, _p(W), _p(bias), _p(residual), ldr, _p(C), ldc, M, N, K, epi, alpha,
              self._stream())
+        self._prof_end(ev)
         self.launches += 1
+
+    def _k(self, tag, name, *args, n=1):
+        """One ABI call = `n` kernel launches on the current stream, optionally event-timed under `tag`."""
+        ev = self._prof_begin(tag)
+        call(name, *args, self._stream())
+        self._prof_end(ev)
+        self.launches += n
+
+    # per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg); off by default
+    def _prof_begin(self, tag):
+        if self.prof is None:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
+        self.prof.setdefault(tag, []).append((e0, e1))
+        return e1
+
+    def _prof_end(self, ev):
+        if ev is not None:
+            ev.record(torch.cuda.current_stream(self.device))
+
+    def profile(self, enable: bool):
+        self.prof = {} if enable else None
+
+    def profile_summary(self) -> Dict[str, Tuple[int, float]]:
+        """tag -> (launch count, total milliseconds); call after a synchronize."""
+        out = {}
+        for tag, evs in (self.prof or {}).items():
+            out[tag] = (len(evs), float(sum(a.elapsed_time(b) for a, b in evs)))
+        return out
 
     def _ln(self, x, gb, y, M, ld=None):
         ld = self.d if ld is None else ld
-        call("masr_layernorm_f32", _p(x), ld, _p(gb[0]), _p(gb[1]), _p(y), ld, M, self.d, 1e-5, self._stream())
-        self.launches += 1
+        self._k("layernorm", "masr_layernorm_f32", _p(x), ld, _p(gb[0]), _p(gb[1]), _p(y), ld, M, self.d, 1e-5)
 
     def _precompute_pos(self):
         """linear_pos(pe) for every layer: input-independent (attention.py:228), done once on the GPU."""
@@ -121,6 +201,16 @@ class ConformerEngine:
             "psum": torch.empty(B, device=dev, dtype=f32),
             "pcount": torch.empty(B, device=dev, dtype=torch.int32),
         }
+        if self.gemm_path == "tc":
+            f16 = torch.float16
+            TH = (F1 + 1) // 2
+            Mx = max(1, M)
+            del ws["c1"], ws["c2"], ws["hid"]
+            ws["c1p"] = (torch.zeros(4 * B * TH * 20 * d, device=dev, dtype=f16), torch.zeros(4 * B * TH * 20 * d, device=dev, dtype=f16))
+            ws["c2p"] = (torch.empty(Mx * self.f2, d, device=dev, dtype=f16), torch.empty(Mx * self.f2, d, device=dev, dtype=f16))
+            ws["t0p"] = (torch.empty(Mx, d, device=dev, dtype=f16), torch.empty(Mx, d, device=dev, dtype=f16))
+            ws["t1p"] = (torch.empty(Mx, d, device=dev, dtype=f16), torch.empty(Mx, d, device=dev, dtype=f16))
+            ws["hidp"] = (torch.empty(Mx, self.w.ffn, device=dev, dtype=f16), torch.empty(Mx, self.w.ffn, device=dev, dtype=f16))
         if len(self._ws) > 8:
             self._ws.clear()
         self._ws[key] = ws
@@ -136,15 +226,26 @@ class ConformerEngine:
         (``wave_dev`` float32[total], ``offsets_dev`` int64[B+1], ``lengths``)."""
         if wave_dev is None:
             lengths = [int(w.shape[0]) for w in waves]
-            offs = np.zeros(len(waves) + 1, np.int64)
+            nb = len(waves)
+            offs = np.zeros(nb + 1, np.int64)
             np.cumsum(lengths, out=offs[1:])
             total = int(offs[-1])
-            host = torch.empty(max(1, total), dtype=torch.float32, pin_memory=True)
-            hv = host.numpy()
+            tail_f = 2 * (nb + 1)                      # int64 offsets ride in the tail of the staging buffer
+            if self._staged is not None:
+                self._staged.synchronize()             # previous async H2D out of this buffer has finished
+            if self._pinned is None or self._pinned.numel() < total + tail_f + 2:
+                n = (int(1.25 * total) + tail_f + 1024) // 2 * 2
+                self._pinned = torch.empty(n, dtype=torch.float32, pin_memory=True)
+            hv = self._pinned.numpy()
             for i, w in enumerate(waves):
                 hv[offs[i]:offs[i + 1]] = w
-            wave_dev = host.to(self.device, non_blocking=True)
-            offsets_dev = torch.from_numpy(offs).pin_memory().to(self.device, non_blocking=True)
+            t0 = (total + 1) // 2 * 2
+            self._pinned[t0:t0 + tail_f].view(torch.int64).copy_(torch.from_numpy(offs))
+            wave_dev = self._pinned[:max(1, total)].to(self.device, non_blocking=True)
+            offsets_dev = self._pinned[t0:t0 + tail_f].view(torch.int64).to(self.device, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(torch.cuda.current_stream(self.device))
+            self.h2d_bytes += 4 * total + 8 * (nb + 1)
         B = len(lengths)
         frames = [num_frames(n) for n in lengths]
         Fmax = max(frames) if frames else 0
@@ -153,18 +254,17 @@ class ConformerEngine:
         feats = torch.empty(B, max(1, Fmax), NUM_MEL, device=dev, dtype=torch.float32)
         status = torch.zeros(B, device=dev, dtype=torch.int32)
         gain = None
-        st = self._stream()
+        self.last_gain = None
         if use_db_normalization:
             nbytes = _lib.C.c_int64(0)
             call("masr_fbank_workspace_bytes", B, max_samples, _lib.C.byref(nbytes))
             scratch = torch.empty(max(8, nbytes.value), device=dev, dtype=torch.uint8)
             gain = torch.empty(B, device=dev, dtype=torch.float32)
-            call("masr_wave_gain_f32", _p(wave_dev), _p(offsets_dev), B, max_samples, float(target_db), 300.0,
-                 _p(gain), _p(status), _p(scratch), st)
-            self.launches += 2
+            self._k("wave_gain", "masr_wave_gain_f32", _p(wave_dev), _p(offsets_dev), B, max_samples, float(target_db),
+                    300.0, _p(gain), _p(status), _p(scratch), n=2)
+            self.last_gain = gain
         if Fmax > 0:
-            call("masr_fbank_f32", _p(wave_dev), _p(offsets_dev), _p(gain), B, Fmax, _p(feats), None, st)
-            self.launches += 1
+            self._k("fbank", "masr_fbank_f32", _p(wave_dev), _p(offsets_dev), _p(gain), B, Fmax, _p(feats), None)
         return feats, frames, status
 
     # ---- encoder -----------------------------------------------------------------------------
@@ -178,64 +278,107 @@ class ConformerEngine:
         ws = self._workspace(B, Fmax)
         if T == 0:
             return ws["x"][:0], tl, 0, ws
-        M, d, st = B * T, self.d, self._stream()
-        tlens = torch.tensor(tl, dtype=torch.int32).pin_memory().to(self.device, non_blocking=True)
-        ws["tlens"] = tlens
+        M, d = B * T, self.d
+        if ws.get("tl_host") != tl:
+            ws["tlens"] = torch.tensor(tl, dtype=torch.int32, device=self.device)
+            ws["tl_host"] = list(tl)
+            self.h2d_bytes += 4 * B
+        tlens = ws["tlens"]
+        if self.gemm_path == "tc":
+            return self._encode_tc(feats, ws, tl, tlens, B, Fmax, F1, T, M)
         # Conv2dSubsampling4 (+ CMVN) -> x * sqrt(d)
-        call("masr_conv1_cmvn_relu_f32", _p(feats), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w), _p(w.conv1_b),
-             _p(ws["c1"]), B, Fmax, w.idim, F1, self.w1_cols, d, st)
-        call("masr_conv2_s2_relu_f32", _p(ws["c1"]), _p(w.conv2_w), _p(w.conv2_b), _p(ws["c2"]), B, F1, self.w1_cols, T,
-             self.f2, d, st)
-        self.launches += 2
+        self._k("conv1", "masr_conv1_cmvn_relu_f32", _p(feats), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w),
+                _p(w.conv1_b), _p(ws["c1"]), B, Fmax, w.idim, F1, self.w1_cols, d)
+        self._k("conv2", "masr_conv2_s2_relu_f32", _p(ws["c1"]), _p(w.conv2_w), _p(w.conv2_b), _p(ws["c2"]), B, F1,
+                self.w1_cols, T, self.f2, d)
         x, t0, t1, g, hid, qkv = ws["x"], ws["t0"], ws["t1"], ws["g"], ws["hid"], ws["qkv"]
-        self._gemm(ws["c2"], self.f2 * d, w.embed_w, w.embed_b, x, d, M, d, self.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5)
+        self._gemm(ws["c2"], self.f2 * d, w.embed_w, w.embed_b, x, d, M, d, self.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5,
+                   tag="embed_linear")
         lpad = (w.kernel - 1) if self.causal else (w.kernel - 1) // 2
         for L in w.layers:
             # macaron FFN: x += 0.5 * W2 silu(W1 LN(x))
             self._ln(x, L.ln_ffm, t0, M)
-            self._gemm(t0, d, L.ffm[0], L.ffm[1], hid, w.ffn, M, w.ffn, d, EPI_BIAS_SILU)
-            self._gemm(hid, w.ffn, L.ffm[2], L.ffm[3], x, d, M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d)
+            self._gemm(t0, d, L.ffm[0], L.ffm[1], hid, w.ffn, M, w.ffn, d, EPI_BIAS_SILU, tag="ffn_w1")
+            self._gemm(hid, w.ffn, L.ffm[2], L.ffm[3], x, d, M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, tag="ffn_w2")
             # rel-pos MHSA
             self._ln(x, L.ln_mha, t0, M)
-            self._gemm(t0, d, L.wqkv, L.bqkv, qkv, 3 * d, M, 3 * d, d)
-            call("masr_relpos_attention_f32", _p(qkv), 3 * d, T, qkv.data_ptr() + 4 * d, qkv.data_ptr() + 8 * d,
-                 3 * d, T, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), _p(t1), d, T, _p(tlens), _p(tlens), B, self.h,
-                 self.dk, T, st)
-            self.launches += 1
-            self._gemm(t1, d, L.wo, L.bo, x, d, M, d, d, EPI_RESIDUAL, 1.0, x, d)
+            self._gemm(t0, d, L.wqkv, L.bqkv, qkv, 3 * d, M, 3 * d, d, tag="qkv_proj")
+            self._k("attention", "masr_relpos_attention_f32", _p(qkv), 3 * d, T, qkv.data_ptr() + 4 * d,
+                    qkv.data_ptr() + 8 * d, 3 * d, T, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), _p(t1), None, None, d, T,
+                    _p(tlens), _p(tlens), B, self.h, self.dk, T)
+            self._gemm(t1, d, L.wo, L.bo, x, d, M, d, d, EPI_RESIDUAL, 1.0, x, d, tag="out_proj")
             # convolution module
             self._ln(x, L.ln_conv, t0, M)
-            self._gemm(t0, d, L.pw1, L.pw1_b, g, d, M, 2 * d, d, EPI_BIAS_GLU)
-            call("masr_dwconv_ln_silu_f32", _p(g), d, T, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]),
-                 _p(L.glu_pad) if self.causal else None, _p(t1), d, T, _p(tlens), B, d, w.kernel, lpad, T, 1e-5, st)
-            self.launches += 1
-            self._gemm(t1, d, L.pw2, L.pw2_b, x, d, M, d, d, EPI_RESIDUAL, 1.0, x, d)
+            self._gemm(t0, d, L.pw1, L.pw1_b, g, d, M, 2 * d, d, EPI_BIAS_GLU, tag="pw1_glu")
+            self._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, T, _p(L.dw), _p(L.dw_b), _p(L.cn[0]),
+                    _p(L.cn[1]), _p(L.glu_pad) if self.causal else None, _p(t1), None, None, d, T, _p(tlens), B, d,
+                    w.kernel, lpad, T, 1e-5)
+            self._gemm(t1, d, L.pw2, L.pw2_b, x, d, M, d, d, EPI_RESIDUAL, 1.0, x, d, tag="pw2")
             # FFN
             self._ln(x, L.ln_ff, t0, M)
-            self._gemm(t0, d, L.ff[0], L.ff[1], hid, w.ffn, M, w.ffn, d, EPI_BIAS_SILU)
-            self._gemm(hid, w.ffn, L.ff[2], L.ff[3], x, d, M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d)
+            self._gemm(t0, d, L.ff[0], L.ff[1], hid, w.ffn, M, w.ffn, d, EPI_BIAS_SILU, tag="ffn_w1")
+            self._gemm(hid, w.ffn, L.ff[2], L.ff[3], x, d, M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, tag="ffn_w2")
             self._ln(x, L.ln_final, x, M)
         self._ln(x, w.after_norm, t0, M)
         return t0[:M], tl, T, ws
 
+    def _encode_tc(self, feats, ws, tl, tlens, B, Fmax, F1, T, M):
+        """Same layer program as ``encode`` with every dense contraction on tcgen05 (FP16x2 split): GEMM inputs
+        travel as fp16 (h,l) pairs written by the producing kernel's epilogue, the residual stream stays fp32."""
+        w, d, tw = self.w, self.d, self._tcw
+        x, g, qkv = ws["x"], ws["g"], ws["qkv"]
+        t0p, t1p, hidp, c1p, c2p = ws["t0p"], ws["t1p"], ws["hidp"], ws["c1p"], ws["c2p"]
+        self._k("conv1", "masr_conv1_cmvn_relu_planes_f16", _p(feats), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w),
+                _p(w.conv1_b), _p(c1p[0]), _p(c1p[1]), B, Fmax, w.idim, F1, self.w1_cols, d)
+        self._k("conv2", "masr_conv2_tc_f16x2", _p(c1p[0]), _p(c1p[1]), _p(tw["conv2"][0]), _p(tw["conv2"][1]),
+                _p(w.conv2_b), None, _p(c2p[0]), _p(c2p[1]), B, F1, T, d)
+        self._tc(c2p, self.f2 * d, tw["embed"], w.embed_b, M, d, self.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5, C=x, ldc=d,
+                 tag="embed_linear")
+        lpad = (w.kernel - 1) if self.causal else (w.kernel - 1) // 2
+        for i, L in enumerate(w.layers):
+            self._ln_split(x, L.ln_ffm, t0p, M)
+            self._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+            self._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
+            self._ln_split(x, L.ln_mha, t0p, M)
+            self._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, ldc=3 * d, tag="qkv_proj")
+            self._k("attention", "masr_relpos_attention_f32", _p(qkv), 3 * d, T, qkv.data_ptr() + 4 * d,
+                    qkv.data_ptr() + 8 * d, 3 * d, T, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]),
+                    d, T, _p(tlens), _p(tlens), B, self.h, self.dk, T)
+            self._tc(t1p, d, tw[i, "wo"], L.bo, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="out_proj")
+            self._ln_split(x, L.ln_conv, t0p, M)
+            self._tc(t0p, d, tw[i, "pw1"], L.pw1_b, M, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d, tag="pw1_glu")
+            self._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, T, _p(L.dw), _p(L.dw_b), _p(L.cn[0]),
+                    _p(L.cn[1]), _p(L.glu_pad) if self.causal else None, None, _p(t1p[0]), _p(t1p[1]), d, T, _p(tlens), B,
+                    d, w.kernel, lpad, T, 1e-5)
+            self._tc(t1p, d, tw[i, "pw2"], L.pw2_b, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="pw2")
+            self._ln_split(x, L.ln_ff, t0p, M)
+            self._tc(t0p, d, tw[i, "ff1"], L.ff[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+            self._tc(hidp, w.ffn, tw[i, "ff2"], L.ff[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
+            self._ln(x, L.ln_final, x, M)
+        self._ln(x, w.after_norm, ws["t0"], M)            # fp32 encoder output (returned / tests)
+        self._ln_split(x, w.after_norm, t0p, M)           # and the pair the CTC head consumes
+        return ws["t0"][:M], tl, T, ws
+
     # ---- CTC head ----------------------------------------------------------------------------
     def ctc_logits(self, enc: torch.Tensor, ws) -> torch.Tensor:
         M = enc.shape[0]
-        self._gemm(enc, self.d, self.w.ctc_w, self.w.ctc_b, ws["logits"], self.Vpad, M, self.V, self.d)
+        if self.gemm_path == "tc":
+            self._tc(ws["t0p"], self.d, self._tcw["ctc"], self.w.ctc_b, M, self.V, self.d, C=ws["logits"], ldc=self.Vpad,
+                     tag="ctc_head")
+        else:
+            self._gemm(enc, self.d, self.w.ctc_w, self.w.ctc_b, ws["logits"], self.Vpad, M, self.V, self.d, tag="ctc_head")
         return ws["logits"]
 
     def ctc_greedy(self, enc: torch.Tensor, out_lens: Sequence[int], T: int, ws, want_probs: bool = False):
         """-> device tensors (tokens [B,T], ntok, psum, pcount, ids [B*T], probs or None)."""
         B = len(out_lens)
         M = B * T
-        st = self._stream()
         logits = self.ctc_logits(enc, ws)
         probs = torch.empty(M, self.V, device=self.device, dtype=torch.float32) if want_probs else None
-        call("masr_ctc_frame_argmax_f32", _p(logits), self.Vpad, M, self.V, _p(ws["ids"]), _p(ws["maxp"]), _p(probs),
-             self.V, st)
-        call("masr_ctc_greedy_collapse", _p(ws["ids"]), _p(ws["maxp"]), T, _p(ws["tlens"]), B, 0, _p(ws["tokens"]),
-             ws["tokens"].shape[1], _p(ws["ntok"]), _p(ws["psum"]), _p(ws["pcount"]), st)
-        self.launches += 2
+        self._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(logits), self.Vpad, M, self.V, _p(ws["ids"]),
+                _p(ws["maxp"]), _p(probs), self.V)
+        self._k("ctc_collapse", "masr_ctc_greedy_collapse", _p(ws["ids"]), _p(ws["maxp"]), T, _p(ws["tlens"]), B, 0,
+                _p(ws["tokens"]), ws["tokens"].shape[1], _p(ws["ntok"]), _p(ws["psum"]), _p(ws["pcount"]))
         return probs
 
     # ---- public batched entry points -----------------------------------------------------------
@@ -252,16 +395,17 @@ class ConformerEngine:
             return GreedyResult([[] for _ in range(B)], [0.0] * B, None, np.zeros(B, np.int32),
                                 None if status is None else status.cpu().numpy())
         self.ctc_greedy(enc, tl, T, ws)
-        # one small D2H: tokens + counters (+ raw frame ids for tests)
+        # small D2H: tokens + counters (+ raw frame ids for tests); .cpu() synchronises the stream
         tok = ws["tokens"].cpu().numpy()
         ntok = ws["ntok"].cpu().numpy()
         psum = ws["psum"].cpu().numpy()
         pcnt = ws["pcount"].cpu().numpy()
+        st_h = None if status is None else status.cpu().numpy()
+        self.d2h_bytes += tok.nbytes + ntok.nbytes + psum.nbytes + pcnt.nbytes + (0 if st_h is None else st_h.nbytes)
         tokens = [tok[b, :ntok[b]].tolist() for b in range(B)]
         scores = [greedy_score(psum[b], pcnt[b]) for b in range(B)]
         fid = ws["ids"][:B * T].view(B, T).cpu().numpy() if return_frames else None
-        return GreedyResult(tokens, scores, fid, np.asarray(tl, np.int32),
-                            None if status is None else status.cpu().numpy())
+        return GreedyResult(tokens, scores, fid, np.asarray(tl, np.int32), st_h)
 
     def posteriors(self, feats_host: np.ndarray, feat_lens: Sequence[int]) -> np.ndarray:
         """The ``InferencePredictor.predict`` seam (inference_predictor.py:52-64): raw features
@@ -322,7 +466,7 @@ class ConformerEngine:
                  kv.data_ptr() + 4 * (st.cache_start + cache_t1) * 2 * d, 2 * d, c, 2 * d, d, EPI_BIAS, 1.0, s)  # k|v appended
             kbase = kv.data_ptr() + 4 * st.cache_start * 2 * d
             call("masr_relpos_attention_f32", _p(q), d, 0, kbase, kbase + 4 * d, 2 * d, 0,
-                 L.ptab.data_ptr() + 4 * pos_start * d, d, _p(L.pos_u), _p(L.pos_v), _p(t1), d, 0, _p(ws["qlen"]),
+                 L.ptab.data_ptr() + 4 * pos_start * d, d, _p(L.pos_u), _p(L.pos_v), _p(t1), None, None, d, 0, _p(ws["qlen"]),
                  _p(ws["klen"]), 1, self.h, self.dk, c, s)
             self.launches += 2
             self._gemm(t1, d, L.wo, L.bo, x, d, c, d, d, EPI_RESIDUAL, 1.0, x, d)
@@ -332,7 +476,7 @@ class ConformerEngine:
                  d, 1e-5, s)
             self.launches += 1
             self._gemm(xc, d, L.pw1, L.pw1_b, g, d, lorder + c, 2 * d, d, EPI_BIAS_GLU)
-            call("masr_dwconv_ln_silu_f32", _p(g), d, 0, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]), None, _p(t1), d, 0,
+            call("masr_dwconv_ln_silu_f32", _p(g), d, 0, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]), None, _p(t1), None, None, d, 0,
                  _p(ws["clen"]), 1, d, w.kernel, 0, c, 1e-5, s)
             self.launches += 1
             # new cnn cache = last `lorder` rows of [cache ++ chunk]; overlapping move -> go through a scratch

@@ -1,0 +1,237 @@
+"""Drop-in for ``masr.predict.MASRPredictor`` (masr/predict.py:19-362) on the B200 engine.
+
+Same constructor arguments, same ``predict`` / ``predict_stream`` / ``reset_stream`` signatures,
+same ``{'text': str, 'score': float}`` results, same YAML keys (``use_model``, ``streaming``,
+``decoder``, ``preprocess_conf``, ``dataset_conf.dataset_vocab``) and the same ``inference.pt``
+weights.  What changes is where the work happens: the waveform goes to the GPU once and only token
+ids + a score come back (the reference featurises on the CPU, copies features up, copies the whole
+[T,V] posterior down and decodes with numpy — predict.py:181-190, inference_predictor.py:59-64).
+
+Additive entry points (the reference API is single-utterance): ``predict_batch``.
+Out of the hot-path scope and therefore explicit errors here: punctuation (``use_pun``), inverse
+text normalisation (``is_itn``), VAD long-audio segmentation (``predict_long``), model download
+(``configs=None``), resampling, and ``use_gpu=False`` (there is no CPU path).
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import yaml
+
+from . import SUPPORT_MODEL
+from .audio import load_audio, pcm_bytes_to_float32, samples_to_float32
+from .engine import ConformerEngine, greedy_score, subsampled_len
+from .text import TextFeaturizer, ids_to_text
+
+logger = logging.getLogger(__name__)
+
+
+class _Cfg(dict):
+    """``dict_to_object`` (masr/utils/utils.py:45-56): attribute access over nested dicts."""
+    __setattr__ = dict.__setitem__
+    __getattr__ = dict.__getitem__
+
+
+def dict_to_object(obj):
+    if not isinstance(obj, dict):
+        return obj
+    out = _Cfg()
+    for k, v in obj.items():
+        out[k] = dict_to_object(v)
+    return out
+
+
+# streaming window arithmetic of predict.py:283-289
+DECODING_CHUNK_SIZE = 16
+CONTEXT = 7
+SUBSAMPLING = 4
+CACHED_FEATURE_NUM = CONTEXT - SUBSAMPLING                         # 3 feature frames carried over
+DECODING_WINDOW = (DECODING_CHUNK_SIZE - 1) * SUBSAMPLING + CONTEXT  # 67
+STRIDE = SUBSAMPLING * DECODING_CHUNK_SIZE                         # 64
+
+
+def chunk_starts(num_frames: int, is_end: bool) -> List[int]:
+    """Start indices of the encoder chunks the reference runs for ``num_frames`` cached feature
+    frames (predict.py:292-303); empty when it would return ``None``."""
+    if num_frames < DECODING_WINDOW and not is_end:
+        return []
+    if num_frames < CONTEXT:
+        return []
+    left = CONTEXT if is_end else DECODING_WINDOW
+    return list(range(0, num_frames - left + 1, STRIDE))
+
+
+class MASRPredictor:
+    def __init__(self,
+                 configs=None,
+                 model_tag='conformer_streaming_fbank_aishell',
+                 model_path='models/conformer_streaming_fbank/inference.pt',
+                 use_pun=False,
+                 pun_model_dir='models/pun_models/',
+                 use_gpu=True):
+        if not configs:
+            raise Exception("masr_b200: model download (configs=None, model_tag=...) is not supported; "
+                            "pass a YAML path or dict plus model_path")
+        if isinstance(configs, str):
+            with open(configs, 'r', encoding='utf-8') as f:
+                configs = yaml.load(f.read(), Loader=yaml.FullLoader)
+        self.configs = dict_to_object(configs)
+        assert self.configs.use_model in SUPPORT_MODEL, f'没有该模型：{self.configs.use_model}'
+        if not use_gpu:
+            raise Exception("masr_b200 has no CPU path: use_gpu=False is not supported")
+        if use_pun:
+            raise Exception("masr_b200: the punctuation model (use_pun) is outside the hot-path scope")
+        self.running = False
+        self.use_gpu = use_gpu
+        self._text_featurizer = TextFeaturizer(vocab_filepath=self.configs.dataset_conf.dataset_vocab)
+        pc = self.configs.preprocess_conf
+        if pc.get('feature_method', 'fbank') != 'fbank' or int(pc.get('n_mels', 80)) != 80:
+            raise Exception("masr_b200 implements the fbank/80-mel front-end of the shipped configs only")
+        self._sample_rate = int(pc.get('sample_rate', 16000))
+        self._use_db = bool(pc.get('use_dB_normalization', True))
+        self._target_db = float(pc.get('target_dB', -20))
+        if self.configs.decoder == 'ctc_beam_search':
+            # the reference falls back to greedy when its external C++ decoder is missing (predict.py:103-109)
+            logger.warning('ctc_beam_search is not wired into MASRPredictor yet; using ctc_greedy')
+            self.configs.decoder = 'ctc_greedy'
+        if not os.path.exists(model_path):
+            raise Exception("模型文件不存在，请检查{}是否存在！".format(model_path))
+        if self.configs.use_model != 'conformer':
+            raise Exception(f"masr_b200: model '{self.configs.use_model}' is not implemented yet (conformer only)")
+        self.predictor = ConformerEngine(model_path, streaming=bool(self.configs.streaming))
+        if self.predictor.V != self._text_featurizer.vocab_size:
+            raise Exception(f"vocabulary has {self._text_featurizer.vocab_size} entries but the model's CTC head has "
+                            f"{self.predictor.V}")
+        # streaming state (predict.py:70-73)
+        self.remained_wav: Optional[np.ndarray] = None
+        self.cached_feat: Optional[torch.Tensor] = None       # device [n, 80]
+        self._stream = self.predictor.new_stream() if self.configs.streaming else None
+        self._hist_ids: List[int] = []
+        self._hist_probs: List[np.float32] = []
+        # warm-up, as the reference does (predict.py:88-93)
+        warmup_audio = np.random.uniform(low=-2.0, high=2.0, size=(134240,))
+        self.predict(audio_data=warmup_audio, is_itn=False)
+        self.reset_stream()
+
+    # ---------------------------------------------------------------------------------------------
+    def _check_rate(self, sr):
+        if sr != self._sample_rate:
+            raise Exception(f"masr_b200: resampling is outside the hot-path scope (got {sr} Hz, model expects "
+                            f"{self._sample_rate} Hz)")
+
+    def _finish(self, text, use_pun, is_itn):
+        if use_pun:
+            logger.warning('标点符号模型没有初始化！')
+        if is_itn:
+            raise Exception("masr_b200: inverse text normalisation (is_itn) is outside the hot-path scope")
+        return text
+
+    def predict(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000):
+        """Whole-utterance recognition (predict.py:167-192)."""
+        samples, sr = load_audio(audio_data, sample_rate)
+        self._check_rate(sr)
+        res = self.predictor.transcribe([samples], self._use_db, self._target_db)
+        self._raise_status(res.status)
+        text = ids_to_text(res.tokens[0], self._text_featurizer.vocab_list)
+        return {'text': self._finish(text, use_pun, is_itn), 'score': res.scores[0]}
+
+    def predict_batch(self, audio_list: Sequence, sample_rate=16000):
+        """Additive: a list of utterances in one GPU pass; element i equals ``predict(audio_list[i])``."""
+        waves = []
+        for a in audio_list:
+            s, sr = load_audio(a, sample_rate)
+            self._check_rate(sr)
+            waves.append(s)
+        res = self.predictor.transcribe(waves, self._use_db, self._target_db)
+        self._raise_status(res.status)
+        vocab = self._text_featurizer.vocab_list
+        return [{'text': ids_to_text(t, vocab), 'score': s} for t, s in zip(res.tokens, res.scores)]
+
+    @staticmethod
+    def _raise_status(status):
+        if status is not None and np.any(status != 0):
+            # AudioSegment.normalize raises ValueError when gain > max_gain_db (audio.py:301-303)
+            raise ValueError("无法将段规范化到目标dB，音频增益已经超过max_gain_db (300.0dB)")
+
+    def predict_long(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000):
+        raise NotImplementedError("predict_long needs the VAD model (masr/infer_utils/vad_predictor.py), which is "
+                                  "outside the hot-path scope (SURVEY.md §8f4)")
+
+    # ---------------------------------------------------------------------------------------------
+    def predict_stream(self, audio_data, is_end=False, use_pun=False, is_itn=False, channels=1, samp_width=2,
+                       sample_rate=16000):
+        """Streaming recognition, one push of audio per call (predict.py:237-343).  Returns ``None``
+        while fewer than 67 feature frames are buffered, else the running ``{'text','score'}``."""
+        if not self.configs.streaming:
+            raise Exception(
+                f"不支持改该模型流式识别，当前模型：{self.configs.use_model}，参数streaming为：{self.configs.streaming}")
+        if isinstance(audio_data, np.ndarray):
+            new = samples_to_float32(audio_data)
+        elif isinstance(audio_data, bytes):
+            new = pcm_bytes_to_float32(audio_data, channels=channels, samp_width=samp_width)
+        else:
+            raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
+        self._check_rate(sample_rate)
+        self.remained_wav = new if self.remained_wav is None else np.concatenate([self.remained_wav, new])
+
+        # featurise everything not yet consumed; the reference dB-normalises the remainder IN PLACE on
+        # every push (predict.py:274 + audio_featurizer.py:49-50), so the carried-over tail keeps the gain
+        eng = self.predictor
+        feats, frames, status = eng.fbank([self.remained_wav], self._use_db, self._target_db)
+        gain = float(eng.last_gain.cpu().numpy()[0]) if self._use_db else 1.0
+        self._raise_status(status.cpu().numpy())
+        nf = frames[0]
+        x_chunk = feats[0, :nf]
+        self.cached_feat = x_chunk if self.cached_feat is None else torch.cat([self.cached_feat, x_chunk], dim=0)
+        tail = self.remained_wav[FRAME_SHIFT * nf:]
+        self.remained_wav = (tail * np.float32(gain)).astype(np.float32) if self._use_db else tail
+
+        num_frames = int(self.cached_feat.shape[0])
+        starts = chunk_starts(num_frames, is_end)
+        if not starts:
+            return None
+        end = None
+        for cur in starts:
+            end = min(cur + DECODING_WINDOW, num_frames)
+            out = eng.encode_chunk(self.cached_feat[cur:end], self._stream,
+                                   required_cache_size=DECODING_CHUNK_SIZE * -1)
+            if out is None:
+                continue
+            ids, maxp, _ = out
+            ids_h = ids.cpu().numpy()
+            mp_h = maxp.cpu().numpy()
+            self._hist_ids.extend(int(i) for i in ids_h)
+            self._hist_probs.extend(mp_h[t] for t in range(len(ids_h)) if ids_h[t] != 0)
+        self.cached_feat = self.cached_feat[end - CACHED_FEATURE_NUM:]
+        # greedy_decoder_chunk re-collapses the whole history (ctc_greedy_decoder.py:81-88)
+        toks, prev = [], None
+        for i in self._hist_ids:
+            if i != prev and i != 0:
+                toks.append(i)
+            prev = i
+        acc = np.float32(0.0)
+        for p in self._hist_probs:
+            acc = np.float32(acc + p)
+        score = greedy_score(acc, len(self._hist_probs))
+        text = ids_to_text(toks, self._text_featurizer.vocab_list)
+        if use_pun and is_end and len(text) > 0:
+            logger.warning('标点符号模型没有初始化！')
+        if is_itn:
+            raise Exception("masr_b200: inverse text normalisation (is_itn) is outside the hot-path scope")
+        return {'text': text, 'score': score}
+
+    def reset_stream(self):
+        """predict.py:346-353."""
+        if self._stream is not None:
+            self._stream.reset()
+        self.remained_wav = None
+        self.cached_feat = None
+        self._hist_ids = []
+        self._hist_probs = []
+
+
+FRAME_SHIFT = 160

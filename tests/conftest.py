@@ -61,11 +61,11 @@ def gpu_engines():
     """Engines keyed by (weight seed, streaming); built lazily, shared by the GPU tests."""
     cache = {}
 
-    def get(seed=0, streaming=True):
+    def get(seed=0, streaming=True, gemm="tc"):
         from masr_b200.engine import ConformerEngine
-        key = (seed, streaming)
+        key = (seed, streaming, gemm)
         if key not in cache:
-            cache[key] = ConformerEngine(synth_weights(seed), streaming=streaming)
+            cache[key] = ConformerEngine(synth_weights(seed), streaming=streaming, gemm=gemm)
         return cache[key]
 
     return get
