@@ -31,7 +31,8 @@ constexpr int TBM = 128, TBN = 128, TBK = 64;
 constexpr int TSTAGES = 3;
 constexpr int TILE_BYTES = TBM * TBK * 2;              // 16 KB: one operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;            // Ah, Al, Wh, Wl
-constexpr int TC_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 constexpr uint32_t TMEM_COLS = 512;                    // 2 x main (ping-pong) + correction accumulator, 128 fp32 columns each (384 -> 512)
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 
@@ -139,34 +140,130 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// One 32-column slice of a finished output row: bias was already added; apply the epilogue and store
+// (fp32 and/or the fp16 (h,l) pair).  `n` is the global column of v[0]; warp-uniform except row_ok.
+__device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[32], int n, int64_t out_row, bool row_ok) {
+    if (n >= p.N || !row_ok) return;
+    const bool vec_c = (p.ldc & 3) == 0;
+    if (p.epi == MASR_EPI_BIAS_GLU) {
+        // interleaved (value, gate) columns -> 16 outputs at column n/2
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * sigmoid_f(v[2 * j + 1]);
+        const int nn = n >> 1;
+        if (p.C) {
+            float* cp = p.C + out_row * p.ldc + nn;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+        if (p.Ch) {
+            __half hh[16], ll[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_f16(o[j], hh[j], ll[j]);
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+                *reinterpret_cast<uint4*>(p.Ch + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&hh[j]);
+                *reinterpret_cast<uint4*>(p.Cl + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&ll[j]);
+            }
+        }
+        return;
+    }
+    switch (p.epi) {
+        case MASR_EPI_BIAS_SILU:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            break;
+        case MASR_EPI_BIAS_RELU:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            break;
+        case MASR_EPI_BIAS_SCALE:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+            break;
+        case MASR_EPI_RESIDUAL: {
+            const float* r = p.residual + out_row * p.ldr + n;
+            const bool vec_r = (p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+            if (n + 31 < p.N && vec_r) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 rv = *reinterpret_cast<const float4*>(r + j);
+                    v[j] = rv.x + p.alpha * v[j]; v[j + 1] = rv.y + p.alpha * v[j + 1];
+                    v[j + 2] = rv.z + p.alpha * v[j + 2]; v[j + 3] = rv.w + p.alpha * v[j + 3];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n + j < p.N) v[j] = r[j] + p.alpha * v[j];
+            }
+            break;
+        }
+        default: break;
+    }
+    const bool full = n + 31 < p.N;
+    if (p.C) {
+        float* cp = p.C + out_row * p.ldc + n;
+        if (full && vec_c) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) cp[j] = v[j];
+        }
+    }
+    if (p.Ch) {
+        __half hh[32], ll[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) split_f16(v[j], hh[j], ll[j]);
+        __half* hp = p.Ch + out_row * p.ldc + n;
+        __half* lp = p.Cl + out_row * p.ldc + n;
+        if (full && (p.ldc & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                *reinterpret_cast<uint4*>(hp + j) = *reinterpret_cast<const uint4*>(&hh[j]);
+                *reinterpret_cast<uint4*>(lp + j) = *reinterpret_cast<const uint4*>(&ll[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) { hp[j] = hh[j]; lp[j] = ll[j]; }
+        }
+    }
+}
+
 // Accumulation: the tensor core adds into its fp32 TMEM accumulator with truncation, so a long K loop
 // drifts (measured: 1.4e-5 abs at K=2048 vs 2e-6 for an fp32 FMA loop).  The main product therefore
 // accumulates in TMEM for at most CHUNK_KB K-blocks (K=256); the epilogue warps drain each chunk into
 // round-to-nearest fp32 registers while the next chunk runs into the other TMEM buffer (ping-pong).
-// The correction product is 2^-11 smaller, so its drift is irrelevant and it stays in TMEM throughout.
+// The correction product is 2^-11 smaller, so its drift is irrelevant and it stays in TMEM for the tile.
+//
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  TMEM holds
+// main[2] (ping-pong by chunk) and corr[2] (ping-pong by tile) = 512 columns, so the MMA warp runs tile
+// i+1 while the 8 epilogue warps finish tile i.
 template <bool CONV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p) {
+tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, int tiles_n, int tiles_t) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TSTAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + TSTAGES;
-    uint64_t* acc_full = empty_bar + TSTAGES;      // [2]
-    uint64_t* acc_empty = acc_full + 2;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* main_full = empty_bar + TSTAGES;     // [2]
+    uint64_t* main_empty = main_full + 2;          // [2]
+    uint64_t* corr_full = main_empty + 2;          // [2]
+    uint64_t* corr_empty = corr_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * TBN;
-    const int m0 = CONV ? 0 : blockIdx.y * TBM;
-    const int conv_t0 = CONV ? blockIdx.y * CONV_TR : 0;
-    const int conv_b = CONV ? blockIdx.z : 0;
     const int nkb = p.K / TBK;
-    const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]); tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
         for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], EPI_WARPS);
+            mbar_init(&corr_full[s], 1); mbar_init(&corr_empty[s], EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -178,193 +275,141 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // tile -> coordinates
+    auto decode = [&](int tile, int& n0, int& m0, int& t0, int& b) {
+        const int nt = tile % tiles_n;
+        const int rest = tile / tiles_n;
+        n0 = nt * TBN;
+        if (CONV) { t0 = (rest % tiles_t) * CONV_TR; b = rest / tiles_t; m0 = 0; }
+        else { m0 = rest * TBM; t0 = 0; b = 0; }
+    };
+
     if (warp == 0) {
         if (lane == 0) {
             constexpr uint32_t a_bytes = CONV ? CONV_ROWS * TBK * 2 : TILE_BYTES;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TSTAGES;
-                mbar_wait(&empty_bar[s], ((kb / TSTAGES) & 1) ^ 1);
-                uint8_t* st = smem + s * STAGE_BYTES;
-                mbar_expect_tx(&full_bar[s], 2 * a_bytes + 2 * TILE_BYTES);
-                if (CONV) {
-                    const int tap = kb >> 2, cj = kb & 3;           // K index = tap*256 + cj*64  (C = 256)
-                    const int kh = tap / 3, kw = tap - kh * 3;
-                    const int plane = (kh & 1) * 2 + (kw & 1);
-                    tma_load_4d(&maps.a[2 * plane], &full_bar[s], st, cj * TBK, kw >> 1, conv_t0 + (kh >> 1), conv_b);
-                    tma_load_4d(&maps.a[2 * plane + 1], &full_bar[s], st + TILE_BYTES, cj * TBK, kw >> 1, conv_t0 + (kh >> 1), conv_b);
-                } else {
-                    tma_load_2d(&maps.a[0], &full_bar[s], st, kb * TBK, m0);
-                    tma_load_2d(&maps.a[1], &full_bar[s], st + TILE_BYTES, kb * TBK, m0);
+            uint32_t kg = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int n0, m0, t0, b;
+                decode(tile, n0, m0, t0, b);
+                for (int kb = 0; kb < nkb; ++kb, ++kg) {
+                    const uint32_t s = kg % TSTAGES;
+                    mbar_wait(&empty_bar[s], ((kg / TSTAGES) & 1) ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], 2 * a_bytes + 2 * TILE_BYTES);
+                    if (CONV) {
+                        const int tap = kb >> 2, cj = kb & 3;       // K index = tap*256 + cj*64  (C = 256)
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        const int plane = (kh & 1) * 2 + (kw & 1);
+                        tma_load_4d(&maps.a[2 * plane], &full_bar[s], st, cj * TBK, kw >> 1, t0 + (kh >> 1), b);
+                        tma_load_4d(&maps.a[2 * plane + 1], &full_bar[s], st + TILE_BYTES, cj * TBK, kw >> 1, t0 + (kh >> 1), b);
+                    } else {
+                        tma_load_2d(&maps.a[0], &full_bar[s], st, kb * TBK, m0);
+                        tma_load_2d(&maps.a[1], &full_bar[s], st + TILE_BYTES, kb * TBK, m0);
+                    }
+                    tma_load_2d(&maps.w[0], &full_bar[s], st + 2 * TILE_BYTES, kb * TBK, n0);
+                    tma_load_2d(&maps.w[1], &full_bar[s], st + 3 * TILE_BYTES, kb * TBK, n0);
                 }
-                tma_load_2d(&maps.w[0], &full_bar[s], st + 2 * TILE_BYTES, kb * TBK, n0);
-                tma_load_2d(&maps.w[1], &full_bar[s], st + 3 * TILE_BYTES, kb * TBK, n0);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 @17, M>>4 @24
             constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-            const uint32_t d_corr = tmem_base + 2 * TBN;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TSTAGES;
-                const int c = kb / CHUNK_KB;
-                const bool first = (kb % CHUNK_KB) == 0;
-                const bool last = (kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1;
-                if (first) {
-                    mbar_wait(&acc_empty[c & 1], ((c >> 1) & 1) ^ 1);   // epilogue drained this buffer (chunk c-2)
-                    tc_fence_after();
-                }
-                const uint32_t d_main = tmem_base + (uint32_t)(c & 1) * TBN;
-                mbar_wait(&full_bar[s], (kb / TSTAGES) & 1);
+            uint32_t kg = 0, cg = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+                mbar_wait(&corr_empty[tl & 1], ((tl >> 1) & 1) ^ 1);    // epilogue has read corr of tile tl-2
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t dAh = umma_desc_k_sw128(sa), dAl = umma_desc_k_sw128(sa + TILE_BYTES);
-                const uint64_t dWh = umma_desc_k_sw128(sa + 2 * TILE_BYTES), dWl = umma_desc_k_sw128(sa + 3 * TILE_BYTES);
+                const uint32_t d_corr = tmem_base + 2 * TBN + (tl & 1) * TBN;
+                for (int kb = 0; kb < nkb; ++kb, ++kg) {
+                    const uint32_t s = kg % TSTAGES;
+                    const bool first = (kb % CHUNK_KB) == 0;
+                    const bool last = (kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1;
+                    if (first) {
+                        mbar_wait(&main_empty[cg & 1], ((cg >> 1) & 1) ^ 1);  // epilogue drained this buffer (chunk cg-2)
+                        tc_fence_after();
+                    }
+                    const uint32_t d_main = tmem_base + (cg & 1) * TBN;
+                    mbar_wait(&full_bar[s], (kg / TSTAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dAh = umma_desc_k_sw128(sa), dAl = umma_desc_k_sw128(sa + TILE_BYTES);
+                    const uint64_t dWh = umma_desc_k_sw128(sa + 2 * TILE_BYTES), dWl = umma_desc_k_sw128(sa + 3 * TILE_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < TBK / 16; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 2);          // 16 halves = 32 B = 2 x 16-byte units
-                    umma_f16(d_main, dAh + adv, dWh + adv, idesc, (first && ks == 0) ? 0u : 1u);
-                    umma_f16(d_corr, dAh + adv, dWl + adv, idesc, (kb | ks) ? 1u : 0u);
-                    umma_f16(d_corr, dAl + adv, dWh + adv, idesc, 1u);
+                    for (int ks = 0; ks < TBK / 16; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);      // 16 halves = 32 B = 2 x 16-byte units
+                        umma_f16(d_main, dAh + adv, dWh + adv, idesc, (first && ks == 0) ? 0u : 1u);
+                        umma_f16(d_corr, dAh + adv, dWl + adv, idesc, (kb | ks) ? 1u : 0u);
+                        umma_f16(d_corr, dAl + adv, dWh + adv, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[s]);                        // slot reusable once these MMAs retire
+                    if (last) { umma_commit(&main_full[cg & 1]); ++cg; }
                 }
-                umma_commit(&empty_bar[s]);                            // slot reusable once these MMAs retire
-                if (last) umma_commit(&acc_full[c & 1]);               // chunk complete (and, for the last one, everything)
+                umma_commit(&corr_full[tl & 1]);                       // whole tile (incl. corrections) complete
             }
         }
     } else {
-        // ---- epilogue warps: TMEM lane quarter = warp % 4 ----
-        const int q = warp & 3;
+        // ---- 8 epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int r_tile = q * 32 + lane;                              // row of the 128-row tile
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        float acc[TBN];
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * (TBN / 2);
+        const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+        uint32_t cg = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            int n0, m0, t0, b;
+            decode(tile, n0, m0, t0, b);
+            float acc[TBN / 2];
 #pragma unroll
-        for (int j = 0; j < TBN; ++j) acc[j] = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-            mbar_wait(&acc_full[c & 1], (c >> 1) & 1);
+            for (int j = 0; j < TBN / 2; ++j) acc[j] = 0.f;
+            for (int c = 0; c < nchunks; ++c, ++cg) {
+                mbar_wait(&main_full[cg & 1], (cg >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < TBN / 64; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_base + (cg & 1) * TBN + cc * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(r[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&main_empty[cg & 1]);
+            }
+            mbar_wait(&corr_full[tl & 1], (tl >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int cc = 0; cc < TBN / 32; ++cc) {
-                uint32_t r[32];
-                tmem_ld32(lane_base + (uint32_t)(c & 1) * TBN + cc * 32, r);
+            for (int cc = 0; cc < TBN / 64; ++cc) {
+                uint32_t rc[32];
+                tmem_ld32(lane_base + 2 * TBN + (tl & 1) * TBN + cc * 32, rc);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(r[j]);
+                for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = fmaf(__uint_as_float(rc[j]), kLoInv, acc[cc * 32 + j]);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[c & 1]);
-        }
-        // row mapping
-        int64_t out_row;
-        bool row_ok;
-        if (CONV) {
-            const int ti = r_tile / CONV_W2, f = r_tile - ti * CONV_W2;
-            const int t = conv_t0 + ti;
-            row_ok = r_tile < CONV_ROWS && t < p.conv_T2;
-            out_row = ((int64_t)conv_b * p.conv_T2 + t) * CONV_W2 + f;
-        } else {
-            out_row = m0 + r_tile;
-            row_ok = out_row < p.M;
-        }
-        const bool vec_c = (p.ldc & 3) == 0;
-        const bool vec_r = (p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+            if (lane == 0) mbar_arrive(&corr_empty[tl & 1]);           // TMEM released: the rest runs from registers
+            // row mapping
+            int64_t out_row;
+            bool row_ok;
+            if (CONV) {
+                const int ti = r_tile / CONV_W2, f = r_tile - ti * CONV_W2;
+                const int t = t0 + ti;
+                row_ok = r_tile < CONV_ROWS && t < p.conv_T2;
+                out_row = ((int64_t)b * p.conv_T2 + t) * CONV_W2 + f;
+            } else {
+                out_row = m0 + r_tile;
+                row_ok = out_row < p.M;
+            }
 #pragma unroll
-        for (int cc = 0; cc < TBN / 32; ++cc) {
-            const int n = n0 + cc * 32;
-            uint32_t rc[32];
-            tmem_ld32(lane_base + 2 * TBN + cc * 32, rc);
-            tmem_ld_wait();
-            if (n < p.N) {                                            // warp-uniform
+            for (int cc = 0; cc < TBN / 64; ++cc) {
+                const int n = n0 + half * (TBN / 2) + cc * 32;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float b = (p.bias != nullptr && n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
-                    v[j] = fmaf(__uint_as_float(rc[j]), kLoInv, acc[cc * 32 + j]) + b;
+                    float bb = (p.bias != nullptr && n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
+                    v[j] = acc[cc * 32 + j] + bb;
                 }
-                if (row_ok && p.epi == MASR_EPI_BIAS_GLU) {
-                    // interleaved (value, gate) columns -> 16 outputs at column n/2
-                    float o[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * sigmoid_f(v[2 * j + 1]);
-                    const int nn = n >> 1;
-                    if (p.C) {
-                        float* cp = p.C + out_row * p.ldc + nn;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                    }
-                    if (p.Ch) {
-                        __half hh[16], ll[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) split_f16(o[j], hh[j], ll[j]);
-#pragma unroll
-                        for (int j = 0; j < 16; j += 8) {
-                            *reinterpret_cast<uint4*>(p.Ch + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&hh[j]);
-                            *reinterpret_cast<uint4*>(p.Cl + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&ll[j]);
-                        }
-                    }
-                } else if (row_ok) {
-                    switch (p.epi) {
-                        case MASR_EPI_BIAS_SILU:
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-                            break;
-                        case MASR_EPI_BIAS_RELU:
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                            break;
-                        case MASR_EPI_BIAS_SCALE:
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-                            break;
-                        case MASR_EPI_RESIDUAL: {
-                            const float* r = p.residual + out_row * p.ldr + n;
-                            if (n + 31 < p.N && vec_r) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    float4 rv = *reinterpret_cast<const float4*>(r + j);
-                                    v[j] = rv.x + p.alpha * v[j]; v[j + 1] = rv.y + p.alpha * v[j + 1];
-                                    v[j + 2] = rv.z + p.alpha * v[j + 2]; v[j + 3] = rv.w + p.alpha * v[j + 3];
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (n + j < p.N) v[j] = r[j] + p.alpha * v[j];
-                            }
-                            break;
-                        }
-                        default: break;
-                    }
-                    const bool full = n + 31 < p.N;
-                    if (p.C) {
-                        float* cp = p.C + out_row * p.ldc + n;
-                        if (full && vec_c) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (n + j < p.N) cp[j] = v[j];
-                        }
-                    }
-                    if (p.Ch) {
-                        __half hh[32], ll[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) split_f16(v[j], hh[j], ll[j]);
-                        __half* hp = p.Ch + out_row * p.ldc + n;
-                        __half* lp = p.Cl + out_row * p.ldc + n;
-                        if (full && (p.ldc & 7) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                *reinterpret_cast<uint4*>(hp + j) = *reinterpret_cast<const uint4*>(&hh[j]);
-                                *reinterpret_cast<uint4*>(lp + j) = *reinterpret_cast<const uint4*>(&ll[j]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (n + j < p.N) { hp[j] = hh[j]; lp[j] = ll[j]; }
-                        }
-                    }
-                }
+                store_chunk(p, v, n, out_row, row_ok);
             }
             __syncwarp();
         }
@@ -445,6 +490,19 @@ static int make_map_plane(CUtensorMap* map, const void* ptr, int B, int TH, int 
     return MASR_OK;
 }
 
+static int num_sms() {
+    static int n[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
+    }
+    return n[dev];
+}
+
 static int ensure_tc_attrs() {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -484,8 +542,10 @@ extern "C" int masr_conv2_tc_f16x2(const void* c1h, const void* c1l, const void*
     if ((rc = make_map_2d(&maps.w[1], Wl, C, 9 * C, 9 * C))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
     TcParams p{bias, nullptr, out, (__half*)outh, (__half*)outl, 0, C, B * T2 * CONV_W2, C, 9 * C, MASR_EPI_BIAS_RELU, 1.f, T2};
-    dim3 grid((C + TBN - 1) / TBN, (T2 + CONV_TR - 1) / CONV_TR, B);
-    tc_gemm_kernel<true><<<grid, TC_THREADS, kTcSmem, (cudaStream_t)stream>>>(maps, p);
+    const int tiles_n = (C + TBN - 1) / TBN, tiles_t = (T2 + CONV_TR - 1) / CONV_TR;
+    const int num_tiles = tiles_n * tiles_t * B;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    tc_gemm_kernel<true><<<grid, TC_THREADS, kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t);
     return check_launch("tc_gemm_kernel<conv>");
 }
 
@@ -521,7 +581,9 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     if ((rc = make_map_2d(&maps.w[1], Wl, N, K, K))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
     TcParams p{bias, residual, C, (__half*)Ch, (__half*)Cl, ldr, ldc, M, N, K, epilogue, alpha, 0};
-    dim3 grid((N + TBN - 1) / TBN, (M + TBM - 1) / TBM);
-    tc_gemm_kernel<false><<<grid, TC_THREADS, kTcSmem, (cudaStream_t)stream>>>(maps, p);
+    const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
+    const int num_tiles = tiles_n * tiles_m;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    tc_gemm_kernel<false><<<grid, TC_THREADS, kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1);
     return check_launch("tc_gemm_kernel");
 }
