@@ -24,6 +24,8 @@ _FLOAT_TYPES = (np.float16, np.float32, np.float64)
 def samples_to_float32(samples: np.ndarray) -> np.ndarray:
     """Integers are scaled to [-1, 1) by 2^-(bits-1); multi-channel input is averaged over channels."""
     samples = np.asarray(samples)
+    if samples.dtype == np.float32 and samples.ndim == 1 and samples.flags.c_contiguous:
+        return samples               # already in the internal format: no copy (the engine never writes into it)
     out = samples.astype(np.float32)
     if samples.dtype in _INT_TYPES:
         out *= np.float32(1.0 / 2 ** (np.iinfo(samples.dtype).bits - 1))

@@ -1,0 +1,299 @@
+// Relative-position attention core on the tensor cores (warp-level mma.sync m16n8k16, fp16 operands,
+// fp32 accumulate) with the same FP16x2 operand split as tc_gemm.cu, flash-style:
+//
+//   S      = [q+u | q+v] . [k | p]^T / sqrt(d_k)          (128-wide contraction; no rel_shift, attention.py:245-247)
+//   out    = softmax_j(S[:, j < klen]) . v
+//   x.y   ~= xh.yh + 2^-11 (xh.yl + xl.yh),   h = fp16(x), l = fp16((x-h) 2^11)   -> fp32-grade results
+//
+// Same contract as relpos_attention_kernel (attention.cu), which stays as the fp32 FMA reference
+// implementation (used by the single-stream chunk path).  One CTA = 64 queries of one (utterance, head),
+// 4 warps x 16 query rows; keys stream through shared memory in tiles of 32; the score tile, the
+// probabilities and the output accumulators never leave registers (the S accumulator fragment of two
+// 8-key blocks is exactly the A fragment of the P.V MMA).
+//
+// Round-1 note: this is the legacy HMMA path (a 5 % FLOP share of the step); the tcgen05 version is future work.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace masr {
+
+constexpr int MQ = 64;        // queries per CTA
+constexpr int MKT = 32;       // keys per tile
+constexpr int MD = 64;        // d_k
+constexpr int KC_STRIDE = 136;  // halves per row of a [*, 128] tile (+8 pad: conflict-free ldmatrix)
+constexpr int V_STRIDE = 72;    // halves per row of a [*, 64] tile
+constexpr float kLo = 2048.0f, kLoI = 1.0f / 2048.0f;
+
+struct AttnMmaParams {
+    const float* Q; int64_t ldq, q_bstride;
+    const float* K; const float* V; int64_t ldk, k_bstride;
+    const float* P; int64_t ldp;
+    const float* pos_u; const float* pos_v;
+    float* O; __half* Oh; __half* Ol; int64_t ldo, o_bstride;
+    const int* q_lens; const int* k_lens;
+    float scale;
+    int max_q;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// split 4 floats and store the h / l halves at dst_h / dst_l (8-byte aligned)
+__device__ __forceinline__ void split_store4(float4 v, __half* dst_h, __half* dst_l) {
+    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    __half2 l0 = __floats2half2_rn((v.x - f0.x) * kLo, (v.y - f0.y) * kLo);
+    __half2 l1 = __floats2half2_rn((v.z - f1.x) * kLo, (v.w - f1.y) * kLo);
+    *reinterpret_cast<uint2*>(dst_h) = make_uint2(pack_h2(h0), pack_h2(h1));
+    *reinterpret_cast<uint2*>(dst_l) = make_uint2(pack_h2(l0), pack_h2(l1));
+}
+
+__global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams p) {
+    // region A: Q tile [64][136] h + l (34816 B), later the K|P tile [32][136] h + l; region B: V tile [32][72] h + l
+    __shared__ __align__(16) __half sA[2 * MQ * KC_STRIDE];
+    __shared__ __align__(16) __half sV[2 * MKT * V_STRIDE];
+    __half* sQh = sA;
+    __half* sQl = sA + MQ * KC_STRIDE;
+    __half* sKh = sA;
+    __half* sKl = sA + MKT * KC_STRIDE;
+    __half* sVh = sV;
+    __half* sVl = sV + MKT * V_STRIDE;
+
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MQ;
+    const int qlen = p.q_lens[b], klen = p.k_lens[b];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t ooff = ((int64_t)b * p.o_bstride + q0) * p.ldo + h * MD;
+
+    if (q0 >= qlen || klen <= 0) {              // padded query tile: deterministic zeros
+        for (int idx = tid; idx < MQ * 16; idx += 128) {
+            const int r = idx >> 4, c = (idx & 15) * 4;
+            if (q0 + r < p.max_q) {
+                if (p.O) *reinterpret_cast<float4*>(p.O + ooff + (int64_t)r * p.ldo + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.Oh) {
+                    *reinterpret_cast<uint2*>(p.Oh + ooff + (int64_t)r * p.ldo + c) = make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2*>(p.Ol + ooff + (int64_t)r * p.ldo + c) = make_uint2(0u, 0u);
+                }
+            }
+        }
+        return;
+    }
+    const int nq = min(MQ, qlen - q0);
+
+    // ---- stage [q+u | q+v] as fp16 pairs, then lift this warp's 16 rows into A fragments ----
+    {
+        const float* qsrc = p.Q + ((int64_t)b * p.q_bstride + q0) * p.ldq + h * MD;
+        for (int idx = tid; idx < MQ * 16; idx += 128) {
+            const int r = idx >> 4, c = (idx & 15) * 4;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f), qu = q, qv = q;
+            if (r < nq) {
+                q = ldg_f4(qsrc + (int64_t)r * p.ldq + c);
+                const float4 u = ldg_f4(p.pos_u + h * MD + c), v = ldg_f4(p.pos_v + h * MD + c);
+                qu = make_float4(q.x + u.x, q.y + u.y, q.z + u.z, q.w + u.w);
+                qv = make_float4(q.x + v.x, q.y + v.y, q.z + v.z, q.w + v.w);
+            }
+            split_store4(qu, sQh + r * KC_STRIDE + c, sQl + r * KC_STRIDE + c);
+            split_store4(qv, sQh + r * KC_STRIDE + MD + c, sQl + r * KC_STRIDE + MD + c);
+        }
+    }
+    __syncthreads();
+    uint32_t qh[8][4], ql[8][4];
+    {
+        const int row = warp * 16 + (lane & 15), colb = (lane >> 4) * 8;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            ldsm_x4(qh[ks], sQh + row * KC_STRIDE + ks * 16 + colb);
+            ldsm_x4(ql[ks], sQl + row * KC_STRIDE + ks * 16 + colb);
+        }
+    }
+    __syncthreads();                            // region A is reused for the K|P tiles from here on
+
+    float om[8][4], oc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { om[i][j] = 0.f; oc[i][j] = 0.f; }
+    float m_row[2] = {-INFINITY, -INFINITY}, l_row[2] = {0.f, 0.f};
+
+    const float* kbase = p.K + (int64_t)b * p.k_bstride * p.ldk + h * MD;
+    const float* vbase = p.V + (int64_t)b * p.k_bstride * p.ldk + h * MD;
+    const float* pbase = p.P + h * MD;
+
+    for (int k0 = 0; k0 < klen; k0 += MKT) {
+        const int nk = min(MKT, klen - k0);
+        // ---- stage the key tile: [k | p] -> sK, v -> sV (fp16 pairs) ----
+        for (int idx = tid; idx < MKT * 32; idx += 128) {
+            const int r = idx >> 5, cc = idx & 31;            // 32 float4 per row: 16 of k, 16 of p
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nk) {
+                v4 = cc < 16 ? ldg_f4(kbase + (int64_t)(k0 + r) * p.ldk + cc * 4)
+                             : ldg_f4(pbase + (int64_t)(k0 + r) * p.ldp + (cc - 16) * 4);
+            }
+            split_store4(v4, sKh + r * KC_STRIDE + cc * 4, sKl + r * KC_STRIDE + cc * 4);
+        }
+        for (int idx = tid; idx < MKT * 16; idx += 128) {
+            const int r = idx >> 4, c = (idx & 15) * 4;
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nk) v4 = ldg_f4(vbase + (int64_t)(k0 + r) * p.ldk + c);
+            split_store4(v4, sVh + r * V_STRIDE + c, sVl + r * V_STRIDE + c);
+        }
+        __syncthreads();
+
+        // ---- S = Qcat . Kcat^T (3 MMAs per k-step per 8-key block) ----
+        float sm[4][4], sc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sm[i][j] = 0.f; sc[i][j] = 0.f; }
+        {
+            // ldmatrix.x4: matrices (keys 0-7,dims 0-7), (keys 0-7,dims 8-15), (keys 8-15,dims 0-7), (keys 8-15,dims 8-15)
+            const int key = (lane >> 4) * 8 + (lane & 7), dim = ((lane >> 3) & 1) * 8;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                for (int np = 0; np < 2; ++np) {               // pairs of 8-key blocks
+                    uint32_t kh4[4], kl4[4];
+                    ldsm_x4(kh4, sKh + (np * 16 + key) * KC_STRIDE + ks * 16 + dim);
+                    ldsm_x4(kl4, sKl + (np * 16 + key) * KC_STRIDE + ks * 16 + dim);
+                    mma16816(sm[2 * np], qh[ks], kh4[0], kh4[1]);
+                    mma16816(sc[2 * np], qh[ks], kl4[0], kl4[1]);
+                    mma16816(sc[2 * np], ql[ks], kh4[0], kh4[1]);
+                    mma16816(sm[2 * np + 1], qh[ks], kh4[2], kh4[3]);
+                    mma16816(sc[2 * np + 1], qh[ks], kl4[2], kl4[3]);
+                    mma16816(sc[2 * np + 1], ql[ks], kh4[2], kh4[3]);
+                }
+            }
+        }
+        // ---- scale, mask by key length, online softmax (rows g and g+8 of this warp's 16) ----
+        float mt[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kc = nb * 8 + 2 * t + (j & 1);
+                float s = fmaf(sc[nb][j], kLoI, sm[nb][j]) * p.scale;
+                s = kc < nk ? s : -INFINITY;
+                sm[nb][j] = s;
+                mt[j >> 1] = fmaxf(mt[j >> 1], s);
+            }
+        float alpha[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mt[r] = fmaxf(mt[r], __shfl_xor_sync(0xffffffffu, mt[r], 1));
+            mt[r] = fmaxf(mt[r], __shfl_xor_sync(0xffffffffu, mt[r], 2));
+            const float m_new = fmaxf(m_row[r], mt[r]);
+            alpha[r] = expf(m_row[r] - m_new);
+            m_row[r] = m_new;
+        }
+        uint32_t ph[2][4], pl[2][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            float pv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                pv[j] = expf(sm[nb][j] - m_row[j >> 1]);
+                rs[j >> 1] += pv[j];
+            }
+            // S fragment (rows g / g+8, keys nb*8 + 2t, +1) -> A fragment of k-step nb/2, halves (nb&1)
+            const __half2 h01 = __floats2half2_rn(pv[0], pv[1]), h23 = __floats2half2_rn(pv[2], pv[3]);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn((pv[0] - f01.x) * kLo, (pv[1] - f01.y) * kLo);
+            const __half2 l23 = __floats2half2_rn((pv[2] - f23.x) * kLo, (pv[3] - f23.y) * kLo);
+            const int j2 = nb >> 1, o = (nb & 1) * 2;
+            ph[j2][o] = pack_h2(h01); ph[j2][o + 1] = pack_h2(h23);
+            pl[j2][o] = pack_h2(l01); pl[j2][o + 1] = pack_h2(l23);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) l_row[r] = l_row[r] * alpha[r] + rs[r];
+#pragma unroll
+        for (int db = 0; db < 8; ++db) {
+            om[db][0] *= alpha[0]; om[db][1] *= alpha[0]; om[db][2] *= alpha[1]; om[db][3] *= alpha[1];
+            oc[db][0] *= alpha[0]; oc[db][1] *= alpha[0]; oc[db][2] *= alpha[1]; oc[db][3] *= alpha[1];
+        }
+        // ---- O += P . V ----
+        {
+            // ldmatrix.x4.trans on V[key][d]: matrices (keys 0-7,d 0-7), (keys 8-15,d 0-7), (keys 0-7,d 8-15), (keys 8-15,d 8-15)
+            const int key = ((lane >> 3) & 1) * 8 + (lane & 7), dcol = (lane >> 4) * 8;
+#pragma unroll
+            for (int j2 = 0; j2 < 2; ++j2) {
+#pragma unroll
+                for (int dp = 0; dp < 4; ++dp) {               // pairs of 8-wide d blocks
+                    uint32_t vh4[4], vl4[4];
+                    ldsm_x4_t(vh4, sVh + (j2 * 16 + key) * V_STRIDE + dp * 16 + dcol);
+                    ldsm_x4_t(vl4, sVl + (j2 * 16 + key) * V_STRIDE + dp * 16 + dcol);
+                    mma16816(om[2 * dp], ph[j2], vh4[0], vh4[1]);
+                    mma16816(oc[2 * dp], ph[j2], vl4[0], vl4[1]);
+                    mma16816(oc[2 * dp], pl[j2], vh4[0], vh4[1]);
+                    mma16816(om[2 * dp + 1], ph[j2], vh4[2], vh4[3]);
+                    mma16816(oc[2 * dp + 1], ph[j2], vl4[2], vl4[3]);
+                    mma16816(oc[2 * dp + 1], pl[j2], vh4[2], vh4[3]);
+                }
+            }
+        }
+        __syncthreads();                        // tile consumed before the next one overwrites it
+    }
+
+    // ---- normalise and store (rows g, g+8; columns db*8 + 2t, +1) ----
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_row[r] += __shfl_xor_sync(0xffffffffu, l_row[r], 1);
+        l_row[r] += __shfl_xor_sync(0xffffffffu, l_row[r], 2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = warp * 16 + g + r * 8;
+        if (q0 + row >= p.max_q) continue;
+        const bool valid = row < nq;
+        const float inv = valid ? 1.0f / l_row[r] : 0.f;
+#pragma unroll
+        for (int db = 0; db < 8; ++db) {
+            const float o0 = valid ? fmaf(oc[db][2 * r], kLoI, om[db][2 * r]) * inv : 0.f;
+            const float o1 = valid ? fmaf(oc[db][2 * r + 1], kLoI, om[db][2 * r + 1]) * inv : 0.f;
+            const int64_t off = ooff + (int64_t)row * p.ldo + db * 8 + 2 * t;
+            if (p.O) *reinterpret_cast<float2*>(p.O + off) = make_float2(o0, o1);
+            if (p.Oh) {
+                const __half2 hh = __floats2half2_rn(o0, o1);
+                const float2 hf = __half22float2(hh);
+                *reinterpret_cast<__half2*>(p.Oh + off) = hh;
+                *reinterpret_cast<__half2*>(p.Ol + off) = __floats2half2_rn((o0 - hf.x) * kLo, (o1 - hf.y) * kLo);
+            }
+        }
+    }
+}
+
+}  // namespace masr
+
+using namespace masr;
+
+extern "C" int masr_relpos_attention_tc(const float* Q, int64_t ldq, int64_t q_bstride, const float* K, const float* V,
+                                        int64_t ldk, int64_t k_bstride, const float* P, int64_t ldp, const float* pos_u,
+                                        const float* pos_v, float* O, void* Oh, void* Ol, int64_t ldo, int64_t o_bstride,
+                                        const int* q_lens, const int* k_lens, int B, int H, int d_k, int max_q,
+                                        void* stream) {
+    if (B == 0 || max_q == 0) return MASR_OK;
+    MASR_REQUIRE(Q && K && V && P && pos_u && pos_v && (O || (Oh && Ol)) && q_lens && k_lens, "masr_relpos_attention_tc: null pointer");
+    MASR_REQUIRE(d_k == MD, "masr_relpos_attention_tc: d_k=%d unsupported (this build: 64)", d_k);
+    MASR_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0,
+                 "masr_relpos_attention_tc: leading dimensions must be multiples of 4");
+    AttnMmaParams p{Q, ldq, q_bstride, K, V, ldk, k_bstride, P, ldp, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, ldo, o_bstride,
+                    q_lens, k_lens, 1.0f / sqrtf((float)d_k), max_q};
+    dim3 grid((max_q + MQ - 1) / MQ, H, B);
+    relpos_attention_mma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("relpos_attention_mma_kernel");
+}

@@ -108,6 +108,17 @@ __device__ __forceinline__ void split_f16(float x, __half& h, __half& l) {
     h = __float2half_rn(x);
     l = __float2half_rn((x - __half2float(h)) * kLoScale);
 }
+// two values at a time: cvt.rn.f16x2.f32 packs a pair per instruction
+__device__ __forceinline__ void split_f16x2(float x0, float x1, __half2& h, __half2& l) {
+    h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    l = __floats2half2_rn((x0 - hf.x) * kLoScale, (x1 - hf.y) * kLoScale);
+}
+// Epilogue activations on the SFU (ex2.approx / rcp.approx, <= 2 ulp each): the accurate expf + IEEE divide
+// cost ~40 instructions per element and made the FFN w_1 epilogue 2.6x longer than its MMA main loop.
+// Absolute error < 2e-7 on silu/sigmoid outputs, inside the fp32-grade budget (tests/test_gpu_tc_gemm.py).
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_silu(float x) { return x * fast_sigmoid(x); }
 
 struct TcParams {
     const float* bias;
@@ -149,7 +160,7 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[32], i
         // interleaved (value, gate) columns -> 16 outputs at column n/2
         float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * sigmoid_f(v[2 * j + 1]);
+        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * fast_sigmoid(v[2 * j + 1]);
         const int nn = n >> 1;
         if (p.C) {
             float* cp = p.C + out_row * p.ldc + nn;
@@ -157,13 +168,13 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[32], i
             for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         }
         if (p.Ch) {
-            __half hh[16], ll[16];
+            __align__(16) __half2 hh[8], ll[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_f16(o[j], hh[j], ll[j]);
+            for (int j = 0; j < 8; ++j) split_f16x2(o[2 * j], o[2 * j + 1], hh[j], ll[j]);
 #pragma unroll
             for (int j = 0; j < 16; j += 8) {
-                *reinterpret_cast<uint4*>(p.Ch + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&hh[j]);
-                *reinterpret_cast<uint4*>(p.Cl + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&ll[j]);
+                *reinterpret_cast<uint4*>(p.Ch + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&hh[j / 2]);
+                *reinterpret_cast<uint4*>(p.Cl + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&ll[j / 2]);
             }
         }
         return;
@@ -171,7 +182,7 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[32], i
     switch (p.epi) {
         case MASR_EPI_BIAS_SILU:
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
             break;
         case MASR_EPI_BIAS_RELU:
 #pragma unroll
@@ -213,21 +224,23 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[32], i
         }
     }
     if (p.Ch) {
-        __half hh[32], ll[32];
+        __align__(16) __half2 hh[16], ll[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) split_f16(v[j], hh[j], ll[j]);
+        for (int j = 0; j < 16; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
         __half* hp = p.Ch + out_row * p.ldc + n;
         __half* lp = p.Cl + out_row * p.ldc + n;
         if (full && (p.ldc & 7) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-                *reinterpret_cast<uint4*>(hp + j) = *reinterpret_cast<const uint4*>(&hh[j]);
-                *reinterpret_cast<uint4*>(lp + j) = *reinterpret_cast<const uint4*>(&ll[j]);
+                *reinterpret_cast<uint4*>(hp + j) = *reinterpret_cast<const uint4*>(&hh[j / 2]);
+                *reinterpret_cast<uint4*>(lp + j) = *reinterpret_cast<const uint4*>(&ll[j / 2]);
             }
         } else {
+            const __half* hs = reinterpret_cast<const __half*>(hh);
+            const __half* ls = reinterpret_cast<const __half*>(ll);
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (n + j < p.N) { hp[j] = hh[j]; lp[j] = ll[j]; }
+                if (n + j < p.N) { hp[j] = hs[j]; lp[j] = ls[j]; }
         }
     }
 }

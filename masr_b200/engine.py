@@ -348,7 +348,7 @@ class ConformerEngine:
             self._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
             self._ln_split(x, L.ln_mha, t0p, M)
             self._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, ldc=3 * d, tag="qkv_proj")
-            self._k("attention", "masr_relpos_attention_f32", _p(qkv), 3 * d, T, qkv.data_ptr() + 4 * d,
+            self._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, T, qkv.data_ptr() + 4 * d,
                     qkv.data_ptr() + 8 * d, 3 * d, T, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]),
                     d, T, _p(tlens), _p(tlens), B, self.h, self.dk, T)
             self._tc(t1p, d, tw[i, "wo"], L.bo, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="out_proj")

@@ -109,6 +109,31 @@ def conformer_state_dict(seed: int = 0,
     return sd
 
 
+def efficient_conformer_state_dict(seed: int = 0, vocab_size: int = DEFAULT_VOCAB_SIZE, **kw) -> Dict[str, np.ndarray]:
+    """EfficientConformer (configs/efficient_conformer.yml + constructor defaults): the Conformer tensors with
+    pos_bias_u/v of blocks 0-3 widened to [4, 192] (grouped attention), depthwise kernel 7 in blocks 4-11, and the
+    (unused at inference, concat_after=False) ``concat_linear`` of the strided block 3
+    (efficient_conformer/encoder.py:124-175, attention.py:27-33)."""
+    sd = conformer_state_dict(seed, vocab_size, **kw)
+    rng = np.random.default_rng(500 + seed)
+    d = sd["encoder.after_norm.weight"].shape[0]
+    h = sd["encoder.encoders.0.self_attn.pos_bias_u"].shape[0]
+    dk = d // h
+    k0 = sd["encoder.encoders.0.conv_module.depthwise_conv.weight"].shape[2]
+    nblocks = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("encoder.encoders."))
+    for i in range(nblocks):
+        p = f"encoder.encoders.{i}."
+        if i <= 3:
+            xav = math.sqrt(6.0 / (h + 3 * dk))
+            sd[p + "self_attn.pos_bias_u"] = _uniform(rng, (h, 3 * dk), xav)
+            sd[p + "self_attn.pos_bias_v"] = _uniform(rng, (h, 3 * dk), xav)
+        else:
+            ks = k0 // 2
+            sd[p + "conv_module.depthwise_conv.weight"] = _uniform(rng, (d, 1, ks), 1.0 / math.sqrt(ks))
+    _linear(rng, sd, "encoder.encoders.3.concat_linear", d, 2 * d)
+    return sd
+
+
 def vocabulary(vocab_size: int = DEFAULT_VOCAB_SIZE) -> List[str]:
     """``<blank>``, ``<unk>``, CJK code points…, one ``<space>``, ``<eos>`` last — the order
     the reference's ``create_data`` writes (masr/trainer.py:480-488)."""

@@ -99,8 +99,9 @@ def test_subsampling_convs(rt):
     assert maxdiff(c2, r2.permute(0, 2, 3, 1)) < 5e-5
 
 
-@pytest.mark.parametrize("lens", [[5], [64, 1], [130, 77, 129], [200]])
-def test_relpos_attention(rt, lens):
+@pytest.mark.parametrize("fn", ["masr_relpos_attention_f32", "masr_relpos_attention_tc"])
+@pytest.mark.parametrize("lens", [[5], [64, 1], [130, 77, 129], [200], [33, 248]])
+def test_relpos_attention(rt, lens, fn):
     g = torch.Generator().manual_seed(sum(lens))
     B, T, H, dk = len(lens), max(lens), 4, 64
     d = H * dk
@@ -110,7 +111,7 @@ def test_relpos_attention(rt, lens):
     qd, pd, ud, vd = qkv.to(rt.dev), Ptab.to(rt.dev), u.to(rt.dev), v.to(rt.dev)
     ld = torch.tensor(lens, dtype=torch.int32, device=rt.dev)
     out = torch.full((B, T, d), float("nan"), device=rt.dev)
-    rt.call("masr_relpos_attention_f32", P(qd), 3 * d, T, qd.data_ptr() + 4 * d, qd.data_ptr() + 8 * d, 3 * d, T,
+    rt.call(fn, P(qd), 3 * d, T, qd.data_ptr() + 4 * d, qd.data_ptr() + 8 * d, 3 * d, T,
             P(pd), d, P(ud), P(vd), P(out), None, None, d, T, P(ld), P(ld), B, H, dk, T, rt.st())
     out = out.cpu()
     for b, n in enumerate(lens):
