@@ -150,6 +150,25 @@ int masr_dwconv_ln_silu_f32(const float* g, int64_t ldg, int64_t g_bstride, cons
                             void* yl, int64_t ldy, int64_t y_bstride, const int* in_lens, int B, int C,
                             int kernel_size, int lpad, int out_rows, float eps, void* stream);
 
+/* masr_dwconv_ln_silu_f32 with a time stride (1 or 2): y[t] reads g[t*stride - lpad + k] — the strided depthwise conv of
+ * the EfficientConformer's block 3 (masr/model_utils/efficient_conformer/convolution.py:40-48, encoder.py:160-175). */
+int masr_dwconv_ln_silu_strided_f32(const float* g, int64_t ldg, int64_t g_bstride, const float* w, const float* bias,
+                                    const float* ln_gamma, const float* ln_beta, const float* pad_vec, float* y, void* yh,
+                                    void* yl, int64_t ldy, int64_t y_bstride, const int* in_lens, int B, int C,
+                                    int kernel_size, int lpad, int stride, int out_rows, float eps, void* stream);
+
+/* GroupedRelPositionMultiHeadedAttention core (masr/model_utils/efficient_conformer/attention.py:35-69,120-182): q/k/v
+ * [B*bstride, ld] and p [>=max_t, H*d_k] row-major; `group` consecutive frames are viewed as H heads of width group*d_k;
+ * frames >= lens[b] read as the reference's zero padding; pos_u/pos_v [H, group*d_k]; outputs for frames < lens[b]. */
+int masr_grouped_attention_f32(const float* Q, const float* K, const float* V, const float* P, int64_t ld, int64_t bstride,
+                               const float* pos_u, const float* pos_v, float* O, void* Oh, void* Ol, const int* lens,
+                               int B, int H, int d_k, int group, int max_t, void* stream);
+
+/* AvgPool1d(2, 2, ceil_mode=True, count_include_pad=False) over time per utterance (efficient_conformer/encoder.py:
+ * 173-175): y[b,t] = mean(x[b,2t], x[b,2t+1]) (single element at an odd tail), rows >= ceil(len/2) are 0. */
+int masr_avgpool2_time_f32(const float* x, int64_t in_bstride, float* y, int64_t out_bstride, const int* lens, int B,
+                           int out_rows, int D, void* stream);
+
 /* ---- CTC head / greedy decode ------------------------------------------------------------------- */
 
 /* softmax statistics of CTCLoss.softmax (masr/model_utils/loss/ctc.py:70) fused with the argmax of

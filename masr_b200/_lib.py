@@ -40,6 +40,10 @@ SIGNATURES = {
                                  _vp, _vp, _i, _i, _i, _i, _vp],
     "masr_dwconv_ln_silu_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i,
                                 _i, _f, _vp],
+    "masr_dwconv_ln_silu_strided_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i,
+                                        _i, _i, _i, _f, _vp],
+    "masr_grouped_attention_f32": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "masr_avgpool2_time_f32": [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp],
     "masr_ctc_frame_argmax_f32": [_vp, _i64, _i, _i, _vp, _vp, _vp, _i64, _vp],
     "masr_ctc_greedy_collapse": [_vp, _vp, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp],
 }

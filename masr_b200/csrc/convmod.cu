@@ -16,7 +16,7 @@
 
 namespace masr {
 
-template <int KS, int TT>
+template <int KS, int TT, int STRIDE>
 __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const float* __restrict__ g, int64_t ldg,
                                                              int64_t g_bstride, const float* __restrict__ w,
                                                              const float* __restrict__ bias,
@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const float* __rest
                                                              __half* __restrict__ yh, __half* __restrict__ yl, int64_t ldy, int64_t y_bstride,
                                                              const int* __restrict__ in_lens, int lpad, int out_rows,
                                                              float eps) {
+    // y[t] = sum_k w[k] * g[t*STRIDE - lpad + k]   (STRIDE 2 = the strided block of the EfficientConformer)
     constexpr int C = 256;
     const int c = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * TT;
     const int in_len = in_lens[b];
@@ -39,15 +40,15 @@ __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const float* __rest
     for (int j = 0; j < TT; ++j) acc[j] = bs;
     const float* gb = g + (int64_t)b * g_bstride * ldg + c;
 #pragma unroll
-    for (int i = 0; i < TT + KS - 1; ++i) {
-        const int tau = t0 - lpad + i;
+    for (int i = 0; i < (TT - 1) * STRIDE + KS; ++i) {
+        const int tau = t0 * STRIDE - lpad + i;
         float v;
         if (tau < 0) v = pv;
         else if (tau >= in_len) v = 0.f;
         else v = __ldg(gb + (int64_t)tau * ldg);
 #pragma unroll
         for (int j = 0; j < TT; ++j) {
-            const int k = i - j;
+            const int k = i - j * STRIDE;
             if (k >= 0 && k < KS) acc[j] = fmaf(wk[k], v, acc[j]);
         }
     }
@@ -107,19 +108,33 @@ extern "C" int masr_dwconv_ln_silu_f32(const float* g, int64_t ldg, int64_t g_bs
                                        const float* pad_vec, float* y, void* yh, void* yl, int64_t ldy, int64_t y_bstride,
                                        const int* in_lens, int B, int C, int kernel_size, int lpad, int out_rows,
                                        float eps, void* stream) {
+    return masr_dwconv_ln_silu_strided_f32(g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, yh, yl, ldy, y_bstride,
+                                           in_lens, B, C, kernel_size, lpad, 1, out_rows, eps, stream);
+}
+
+extern "C" int masr_dwconv_ln_silu_strided_f32(const float* g, int64_t ldg, int64_t g_bstride, const float* w,
+                                               const float* bias, const float* ln_gamma, const float* ln_beta,
+                                               const float* pad_vec, float* y, void* yh, void* yl, int64_t ldy,
+                                               int64_t y_bstride, const int* in_lens, int B, int C, int kernel_size,
+                                               int lpad, int stride, int out_rows, float eps, void* stream) {
     if (B == 0 || out_rows == 0) return MASR_OK;
     MASR_REQUIRE(g && w && bias && ln_gamma && ln_beta && (y || (yh && yl)) && in_lens, "masr_dwconv_ln_silu_f32: null pointer");
     MASR_REQUIRE(C == 256, "masr_dwconv_ln_silu_f32: C=%d unsupported (this build: 256)", C);
     constexpr int TT = 8;
     dim3 grid((out_rows + TT - 1) / TT, B);
     cudaStream_t st = (cudaStream_t)stream;
-#define MASR_DW_LAUNCH(KS)                                                                                       \
-    dwconv_ln_silu_kernel<KS, TT><<<grid, 256, 0, st>>>(g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
-                                                        (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps)
+#define MASR_DW_LAUNCH(KS, S)                                                                                       \
+    dwconv_ln_silu_kernel<KS, TT, S><<<grid, 256, 0, st>>>(g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
+                                                           (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps)
+    MASR_REQUIRE(stride == 1 || stride == 2, "masr_dwconv_ln_silu: stride %d unsupported (1/2)", stride);
+    if (stride == 2) {
+        MASR_REQUIRE(kernel_size == 15, "masr_dwconv_ln_silu: stride 2 is built for kernel size 15 only");
+        MASR_DW_LAUNCH(15, 2);
+    } else
     switch (kernel_size) {
-        case 7: MASR_DW_LAUNCH(7); break;
-        case 15: MASR_DW_LAUNCH(15); break;
-        case 31: MASR_DW_LAUNCH(31); break;
+        case 7: MASR_DW_LAUNCH(7, 1); break;
+        case 15: MASR_DW_LAUNCH(15, 1); break;
+        case 31: MASR_DW_LAUNCH(31, 1); break;
         default:
             set_last_error("masr_dwconv_ln_silu_f32: unsupported kernel size %d (7/15/31)", kernel_size);
             return MASR_ERR_INVALID_ARGUMENT;

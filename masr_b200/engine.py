@@ -397,6 +397,10 @@ class ConformerEngine:
         feats, frames, status = self.fbank(waves, use_db_normalization, target_db)
         return self.transcribe_features(feats, frames, status, return_frames)
 
+    def final_len(self, t: int) -> int:
+        """Encoder output frames for `t` subsampled frames (identity here; halved by strided/reduced models)."""
+        return t
+
     # ---- CUDA-graph replay of the device step (launch-bound otherwise: ~190 launches per step) ------------
     GRAPH_FRAME_QUANTUM = 32      # Fmax is rounded up so ragged batches share graphs; padding never changes results
 
@@ -473,8 +477,9 @@ class ConformerEngine:
         Fmax = max(frames)
         q = self.GRAPH_FRAME_QUANTUM
         Fpad = max(q, (Fmax + q - 1) // q * q)
-        T = subsampled_len(Fpad)
-        tl = [subsampled_len(f) for f in frames]
+        T = self.final_len(subsampled_len(Fpad))
+        tl1 = [subsampled_len(f) for f in frames]
+        tl = [self.final_len(t) for t in tl1]
         if max(tl) == 0:
             return GreedyResult([[] for _ in range(B)], [0.0] * B, None, np.zeros(B, np.int32), np.zeros(B, np.int32))
         g = self._graph_for(B, Fpad, use_db, target_db)
@@ -494,7 +499,7 @@ class ConformerEngine:
         po = self._pinned[t0:t0 + 2 * (B + 1)].view(torch.int64)
         po.copy_(torch.from_numpy(offs))
         pt = self._pinned[t0 + 2 * (B + 1):t0 + 2 * (B + 1) + B].view(torch.int32)
-        pt.copy_(torch.tensor(tl, dtype=torch.int32))
+        pt.copy_(torch.tensor(tl1, dtype=torch.int32))
         g["wave"][:total].copy_(self._pinned[:total], non_blocking=True)
         g["offs"].copy_(po, non_blocking=True)
         g["tlens"].copy_(pt, non_blocking=True)
@@ -699,3 +704,98 @@ def greedy_score(psum: np.float32, pcount: int) -> float:
     if int(pcount) == 0:
         return 0
     return float(np.float32(np.float32(psum) / np.float32(int(pcount)))) * 100.0
+
+
+class EfficientConformerEngine(ConformerEngine):
+    """EfficientConformer (configs/efficient_conformer.yml; masr/model_utils/efficient_conformer/encoder.py:25-265):
+    Conformer blocks with grouped attention in blocks 0-3 (group 3), a strided conv module in block 3
+    (T -> ceil(T/2), AvgPool residual) and depthwise kernel 7 from block 4 on; the output is at 80 ms frames.
+    Whole-utterance (batched) path only; tensor-core GEMMs."""
+
+    STRIDE_LAYER = 3
+    GROUP = 3
+
+    def __init__(self, weights_src, streaming: bool = True, device: str = "cuda", max_len: int = 5000, gemm: str = "tc",
+                 use_graphs: bool = True):
+        if gemm != "tc":
+            raise ValueError("EfficientConformerEngine implements the tensor-core path only")
+        super().__init__(weights_src, streaming, device, max_len, gemm, use_graphs)
+        # blocks after the strided one see pos_emb[:, ::2] (encoder.py:257): their linear_pos table comes from pe[::2]
+        pe2 = self.w.pe[::2].contiguous()
+        for i, L in enumerate(self.w.layers):
+            if i > self.STRIDE_LAYER:
+                L.ptab = torch.empty(pe2.shape[0], self.d, device=self.device, dtype=torch.float32)
+                self._gemm(pe2, self.d, L.wpos, None, L.ptab, self.d, pe2.shape[0], self.d, self.d)
+        torch.cuda.synchronize(self.device)
+
+    def final_len(self, t: int) -> int:
+        return (t + 1) // 2
+
+    def new_stream(self):
+        raise NotImplementedError("chunk (streaming) decoding is implemented for the Conformer only so far")
+
+    def encode_chunk(self, *a, **k):
+        raise NotImplementedError("chunk (streaming) decoding is implemented for the Conformer only so far")
+
+    def _encode_tc(self, feats, ws, tl, tlens, B, Fmax, F1, T, M):
+        w, d, tw = self.w, self.d, self._tcw
+        x, g, qkv = ws["x"], ws["g"], ws["qkv"]
+        t0p, t1p, hidp, c1p, c2p = ws["t0p"], ws["t1p"], ws["hidp"], ws["c1p"], ws["c2p"]
+        T2 = self.final_len(T)
+        if "tlens2" not in ws:
+            ws["tlens2"] = torch.zeros(B, device=self.device, dtype=torch.int32)
+        tlens2 = ws["tlens2"]
+        torch.div(tlens + 1, 2, rounding_mode="floor", out=tlens2)
+        self._k("conv1", "masr_conv1_cmvn_relu_planes_f16", _p(feats), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w),
+                _p(w.conv1_b), _p(c1p[0]), _p(c1p[1]), B, Fmax, w.idim, F1, self.w1_cols, d)
+        self._k("conv2", "masr_conv2_tc_f16x2", _p(c1p[0]), _p(c1p[1]), _p(tw["conv2"][0]), _p(tw["conv2"][1]),
+                _p(w.conv2_b), None, _p(c2p[0]), _p(c2p[1]), B, F1, T, d)
+        self._tc(c2p, self.f2 * d, tw["embed"], w.embed_b, M, d, self.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5, C=x, ldc=d,
+                 tag="embed_linear")
+        qb, kb, vb = qkv.view(-1)[:M * d].view(M, d), qkv.view(-1)[M * d:2 * M * d].view(M, d), qkv.view(-1)[2 * M * d:3 * M * d].view(M, d)
+        cur_T, cur_M, cur_lens = T, M, tlens
+        for i, L in enumerate(w.layers):
+            Mi, Ti = cur_M, cur_T
+            lpad = (L.kernel - 1) if self.causal else (L.kernel - 1) // 2
+            self._ln_split(x, L.ln_ffm, t0p, Mi)
+            self._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], Mi, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+            self._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], Mi, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
+            self._ln_split(x, L.ln_mha, t0p, Mi)
+            if L.grouped:
+                wh, wl = tw[i, "qkv"]
+                for j, dst in enumerate((qb, kb, vb)):
+                    self._tc(t0p, d, (wh[j * d:(j + 1) * d], wl[j * d:(j + 1) * d]), L.bqkv[j * d:(j + 1) * d], Mi, d, d,
+                             C=dst, ldc=d, tag="qkv_proj")
+                self._k("attention", "masr_grouped_attention_f32", _p(qb), _p(kb), _p(vb), _p(L.ptab), d, Ti, _p(L.pos_u),
+                        _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), _p(cur_lens), B, self.h, self.dk, self.GROUP, Ti)
+            else:
+                self._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, ldc=3 * d, tag="qkv_proj")
+                self._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, Ti, qkv.data_ptr() + 4 * d,
+                        qkv.data_ptr() + 8 * d, 3 * d, Ti, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]),
+                        _p(t1p[1]), d, Ti, _p(cur_lens), _p(cur_lens), B, self.h, self.dk, Ti)
+            self._tc(t1p, d, tw[i, "wo"], L.bo, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="out_proj")
+            self._ln_split(x, L.ln_conv, t0p, Mi)
+            self._tc(t0p, d, tw[i, "pw1"], L.pw1_b, Mi, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d, tag="pw1_glu")
+            pad_vec = _p(L.glu_pad) if self.causal else None
+            if i == self.STRIDE_LAYER:
+                M2 = B * T2
+                self._k("dwconv_ln_silu", "masr_dwconv_ln_silu_strided_f32", _p(g), d, Ti, _p(L.dw), _p(L.dw_b), _p(L.cn[0]),
+                        _p(L.cn[1]), pad_vec, None, _p(t1p[0]), _p(t1p[1]), d, T2, _p(cur_lens), B, d, L.kernel, lpad, 2, T2,
+                        1e-5)
+                self._k("avgpool", "masr_avgpool2_time_f32", _p(x), Ti, _p(ws["t0"]), T2, _p(cur_lens), B, T2, d)
+                self._tc(t1p, d, tw[i, "pw2"], L.pw2_b, M2, d, d, EPI_RESIDUAL, 1.0, ws["t0"], d, C=x, ldc=d, tag="pw2")
+                cur_T, cur_M, cur_lens = T2, M2, tlens2
+                Mi, Ti = cur_M, cur_T
+            else:
+                self._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, Ti, _p(L.dw), _p(L.dw_b), _p(L.cn[0]),
+                        _p(L.cn[1]), pad_vec, None, _p(t1p[0]), _p(t1p[1]), d, Ti, _p(cur_lens), B, d, L.kernel, lpad, Ti, 1e-5)
+                self._tc(t1p, d, tw[i, "pw2"], L.pw2_b, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="pw2")
+            self._ln_split(x, L.ln_ff, t0p, Mi)
+            self._tc(t0p, d, tw[i, "ff1"], L.ff[1], Mi, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+            self._tc(hidp, w.ffn, tw[i, "ff2"], L.ff[3], Mi, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
+            self._ln(x, L.ln_final, x, Mi)
+        self._ln(x, w.after_norm, ws["t0"], cur_M)
+        self._ln_split(x, w.after_norm, t0p, cur_M)
+        ws["tlens"] = tlens2
+        ws["tl_host"] = None
+        return ws["t0"][:cur_M], [self.final_len(t) for t in tl], cur_T, ws

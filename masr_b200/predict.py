@@ -24,7 +24,7 @@ import yaml
 
 from . import SUPPORT_MODEL
 from .audio import load_audio, pcm_bytes_to_float32, samples_to_float32
-from .engine import ConformerEngine, greedy_score, subsampled_len
+from .engine import ConformerEngine, EfficientConformerEngine, greedy_score, subsampled_len
 from .text import TextFeaturizer, ids_to_text
 
 logger = logging.getLogger(__name__)
@@ -100,16 +100,19 @@ class MASRPredictor:
             self.configs.decoder = 'ctc_greedy'
         if not os.path.exists(model_path):
             raise Exception("模型文件不存在，请检查{}是否存在！".format(model_path))
-        if self.configs.use_model != 'conformer':
-            raise Exception(f"masr_b200: model '{self.configs.use_model}' is not implemented yet (conformer only)")
-        self.predictor = ConformerEngine(model_path, streaming=bool(self.configs.streaming))
+        engines = {'conformer': ConformerEngine, 'efficient_conformer': EfficientConformerEngine}
+        if self.configs.use_model not in engines:
+            raise Exception(f"masr_b200: model '{self.configs.use_model}' is not implemented yet "
+                            f"(available: {sorted(engines)})")
+        self.predictor = engines[self.configs.use_model](model_path, streaming=bool(self.configs.streaming))
+        self._can_stream = self.configs.use_model == 'conformer'
         if self.predictor.V != self._text_featurizer.vocab_size:
             raise Exception(f"vocabulary has {self._text_featurizer.vocab_size} entries but the model's CTC head has "
                             f"{self.predictor.V}")
         # streaming state (predict.py:70-73)
         self.remained_wav: Optional[np.ndarray] = None
         self.cached_feat: Optional[torch.Tensor] = None       # device [n, 80]
-        self._stream = self.predictor.new_stream() if self.configs.streaming else None
+        self._stream = self.predictor.new_stream() if (self.configs.streaming and self._can_stream) else None
         self._hist_ids: List[int] = []
         self._hist_probs: List[np.float32] = []
         # warm-up, as the reference does (predict.py:88-93)
@@ -169,6 +172,8 @@ class MASRPredictor:
         if not self.configs.streaming:
             raise Exception(
                 f"不支持改该模型流式识别，当前模型：{self.configs.use_model}，参数streaming为：{self.configs.streaming}")
+        if not self._can_stream:
+            raise NotImplementedError(f"masr_b200: predict_stream is not implemented for '{self.configs.use_model}' yet")
         if isinstance(audio_data, np.ndarray):
             new = samples_to_float32(audio_data)
         elif isinstance(audio_data, bytes):

@@ -109,12 +109,13 @@ def conformer_state_dict(seed: int = 0,
     return sd
 
 
-def efficient_conformer_state_dict(seed: int = 0, vocab_size: int = DEFAULT_VOCAB_SIZE, **kw) -> Dict[str, np.ndarray]:
+def efficient_conformer_state_dict(seed: int = 0, vocab_size: int = DEFAULT_VOCAB_SIZE, blank_bias: float = 8.5,
+                                   **kw) -> Dict[str, np.ndarray]:
     """EfficientConformer (configs/efficient_conformer.yml + constructor defaults): the Conformer tensors with
     pos_bias_u/v of blocks 0-3 widened to [4, 192] (grouped attention), depthwise kernel 7 in blocks 4-11, and the
     (unused at inference, concat_after=False) ``concat_linear`` of the strided block 3
     (efficient_conformer/encoder.py:124-175, attention.py:27-33)."""
-    sd = conformer_state_dict(seed, vocab_size, **kw)
+    sd = conformer_state_dict(seed, vocab_size, blank_bias=blank_bias, **kw)
     rng = np.random.default_rng(500 + seed)
     d = sd["encoder.after_norm.weight"].shape[0]
     h = sd["encoder.encoders.0.self_attn.pos_bias_u"].shape[0]

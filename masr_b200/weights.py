@@ -83,6 +83,8 @@ class ConformerLayerWeights:
     ff: tuple = None
     ln_final: tuple = None
     ptab: torch.Tensor = None   # linear_pos(pe) [max_len, d], filled by the engine
+    kernel: int = 15            # depthwise kernel size of this block
+    grouped: bool = False       # EfficientConformer grouped attention (pos_bias [h, group*d_k])
 
 
 @dataclass
@@ -163,7 +165,9 @@ def pack_conformer(sd: Dict[str, torch.Tensor], device, max_len: int = 5000) -> 
         L.pw1_b = D(torch.stack([pb1[:d], pb1[d:]], dim=1).reshape(2 * d))
         # what a zero (left-padding) input frame becomes after pointwise_conv1 + GLU (convolution.py:103,117-118)
         L.glu_pad = D(torch.nn.functional.glu(pb1.reshape(1, 2 * d, 1), dim=1).reshape(d))
-        L.dw = D(sd[c + "depthwise_conv.weight"].reshape(d, kernel))
+        L.kernel = int(sd[c + "depthwise_conv.weight"].shape[2])
+        L.grouped = int(sd[a + "pos_bias_u"].shape[1]) != d // h
+        L.dw = D(sd[c + "depthwise_conv.weight"].reshape(d, L.kernel))
         L.dw_b = D(sd[c + "depthwise_conv.bias"])
         L.cn = ln(c + "norm")
         L.pw2 = D(sd[c + "pointwise_conv2.weight"].reshape(d, d))
