@@ -124,6 +124,28 @@ int masr_layernorm_f32(const float* x, int64_t ldx, const float* gamma, const fl
 int masr_layernorm_split_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, void* yh, void* yl,
                              int64_t ldy, int M, int D, float eps, void* stream);
 
+/* Squeezeformer helpers.
+ *  masr_layernorm_ada_split_f16: y = LayerNorm(x) (optional fp32 copy) and the fp16 pair of ada_scale*y+ada_bias — the
+ *    post-norm + adaptive scale of the next sub-module input (squeezeformer/encoder.py:412-463, positionwise.py:57-58);
+ *  masr_affine_split_f16: pair of scale*x+bias (scale/bias optional), elementwise;
+ *  masr_dwconv_bn_silu_f32: conv-module middle with BatchNorm1d(eval) folded to bn_scale/bn_shift (convolution.py:136-142);
+ *  masr_time_reduce_dw_split_f16 / masr_upsample2_add_f32: time reduction depthwise conv (stride 2, kernel 1 or 5) and
+ *    recovery `saved[t] + z[t/2]` (time_reduction.py:53-76,174-197; encoder.py:198-204). */
+int masr_layernorm_ada_split_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, float* y,
+                                 const float* ada_scale, const float* ada_bias, void* yh, void* yl, int64_t ldy, int M, int D,
+                                 float eps, void* stream);
+int masr_affine_split_f16(const float* x, const float* scale, const float* bias, void* yh, void* yl, int64_t M, int D,
+                          void* stream);
+int masr_dwconv_bn_silu_f32(const float* g, int64_t ldg, int64_t g_bstride, const float* w, const float* bias,
+                            const float* bn_scale, const float* bn_shift, const float* pad_vec, float* y, void* yh, void* yl,
+                            int64_t ldy, int64_t y_bstride, const int* in_lens, int B, int C, int kernel_size, int lpad,
+                            int out_rows, void* stream);
+int masr_time_reduce_dw_split_f16(const float* x, int64_t in_bstride, const float* w, const float* bias, void* yh, void* yl,
+                                  int64_t out_bstride, const int* lens, int B, int out_rows, int k, int pad, int D,
+                                  void* stream);
+int masr_upsample2_add_f32(const float* saved, const float* z, float* out, int64_t full_bstride, int64_t half_bstride, int B,
+                           int rows, int D, void* stream);
+
 /* RelPositionMultiHeadedAttention core (masr/model_utils/conformer/attention.py:230-251,107-118):
  * Q rows (b*q_bstride + i), K/V rows (b*k_bstride + j), head h at column h*d_k; P [>=max klen, ldp] =
  * linear_pos(pos_emb) rows aligned with key index j; pos_u/pos_v [H,d_k]; O like Q.

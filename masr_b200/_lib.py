@@ -34,6 +34,11 @@ SIGNATURES = {
     "masr_conv2_tc_f16x2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "masr_layernorm_f32": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
     "masr_layernorm_split_f16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
+    "masr_layernorm_ada_split_f16": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
+    "masr_affine_split_f16": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
+    "masr_dwconv_bn_silu_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i, _i, _vp],
+    "masr_time_reduce_dw_split_f16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
+    "masr_upsample2_add_f32": [_vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp],
     "masr_relpos_attention_f32": [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                   _vp, _vp, _i, _i, _i, _i, _vp],
     "masr_relpos_attention_tc": [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64,

@@ -16,7 +16,7 @@
 
 namespace masr {
 
-template <int KS, int TT, int STRIDE>
+template <int KS, int TT, int STRIDE, bool AFFINE>
 __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const float* __restrict__ g, int64_t ldg,
                                                              int64_t g_bstride, const float* __restrict__ w,
                                                              const float* __restrict__ bias,
@@ -83,12 +83,17 @@ __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const float* __rest
     }
     __syncthreads();
     const float gg = __ldg(ln_g + c), bb = __ldg(ln_b + c);
+    if (AFFINE) {
+        // BatchNorm1d(eval) folded by the caller: ln_g = gamma / sqrt(running_var + eps), ln_b = beta - running_mean * ln_g
+#pragma unroll
+        for (int j = 0; j < TT; ++j) { dev[j] = acc[j]; }
+    }
     const int64_t yoff = (int64_t)b * y_bstride * ldy + c;
 #pragma unroll
     for (int j = 0; j < TT; ++j) {
         const int t = t0 + j;
         if (t < out_rows) {
-            const float o = silu_f(dev[j] * stat[j] * gg + bb);
+            const float o = AFFINE ? silu_f(dev[j] * gg + bb) : silu_f(dev[j] * stat[j] * gg + bb);
             if (y) y[yoff + (int64_t)t * ldy] = o;
             if (yh) {
                 const __half hh = __float2half_rn(o);
@@ -124,7 +129,7 @@ extern "C" int masr_dwconv_ln_silu_strided_f32(const float* g, int64_t ldg, int6
     dim3 grid((out_rows + TT - 1) / TT, B);
     cudaStream_t st = (cudaStream_t)stream;
 #define MASR_DW_LAUNCH(KS, S)                                                                                       \
-    dwconv_ln_silu_kernel<KS, TT, S><<<grid, 256, 0, st>>>(g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
+    dwconv_ln_silu_kernel<KS, TT, S, false><<<grid, 256, 0, st>>>(g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
                                                            (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps)
     MASR_REQUIRE(stride == 1 || stride == 2, "masr_dwconv_ln_silu: stride %d unsupported (1/2)", stride);
     if (stride == 2) {
@@ -141,4 +146,32 @@ extern "C" int masr_dwconv_ln_silu_strided_f32(const float* g, int64_t ldg, int6
     }
 #undef MASR_DW_LAUNCH
     return check_launch("dwconv_ln_silu_kernel");
+}
+
+// Squeezeformer conv-module middle (squeezeformer/convolution.py:136-142): depthwise Conv1d(k) -> BatchNorm1d (eval mode,
+// folded by the caller into per-channel scale/shift) -> SiLU.  Same padding contract as masr_dwconv_ln_silu_f32.
+extern "C" int masr_dwconv_bn_silu_f32(const float* g, int64_t ldg, int64_t g_bstride, const float* w, const float* bias,
+                                       const float* bn_scale, const float* bn_shift, const float* pad_vec, float* y, void* yh,
+                                       void* yl, int64_t ldy, int64_t y_bstride, const int* in_lens, int B, int C,
+                                       int kernel_size, int lpad, int out_rows, void* stream) {
+    if (B == 0 || out_rows == 0) return MASR_OK;
+    MASR_REQUIRE(g && w && bias && bn_scale && bn_shift && (y || (yh && yl)) && in_lens, "masr_dwconv_bn_silu_f32: null pointer");
+    MASR_REQUIRE(C == 256, "masr_dwconv_bn_silu_f32: C=%d unsupported (this build: 256)", C);
+    constexpr int TT = 8;
+    dim3 grid((out_rows + TT - 1) / TT, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kernel_size) {
+        case 15:
+            dwconv_ln_silu_kernel<15, TT, 1, true><<<grid, 256, 0, st>>>(g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
+                (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, 0.f);
+            break;
+        case 31:
+            dwconv_ln_silu_kernel<31, TT, 1, true><<<grid, 256, 0, st>>>(g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
+                (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, 0.f);
+            break;
+        default:
+            set_last_error("masr_dwconv_bn_silu_f32: unsupported kernel size %d (15/31)", kernel_size);
+            return MASR_ERR_INVALID_ARGUMENT;
+    }
+    return check_launch("dwconv_bn_silu_kernel");
 }

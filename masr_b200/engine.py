@@ -70,7 +70,7 @@ class ConformerEngine:
         torch.cuda.set_device(self.device)
         call("masr_check_device")
         sd = load_state_dict(weights_src)
-        self.w: ConformerWeights = pack_conformer(sd, self.device, max_len)
+        self.w: ConformerWeights = self._pack(sd, max_len)
         self.causal = bool(streaming)      # model.py:35-39: streaming -> causal conv + dynamic chunk
         self.d, self.h = self.w.d_model, self.w.heads
         self.dk = self.d // self.h
@@ -90,6 +90,9 @@ class ConformerEngine:
         self._tcw = {}
         if self.gemm_path == "tc":
             self._split_weights()
+
+    def _pack(self, sd, max_len):
+        return pack_conformer(sd, self.device, max_len)
 
     # ---- tensor-core path helpers ---------------------------------------------------------------
     def _split(self, x: torch.Tensor):

@@ -100,7 +100,9 @@ class MASRPredictor:
             self.configs.decoder = 'ctc_greedy'
         if not os.path.exists(model_path):
             raise Exception("模型文件不存在，请检查{}是否存在！".format(model_path))
-        engines = {'conformer': ConformerEngine, 'efficient_conformer': EfficientConformerEngine}
+        from .squeezeformer import SqueezeformerEngine
+        engines = {'conformer': ConformerEngine, 'efficient_conformer': EfficientConformerEngine,
+                   'squeezeformer': SqueezeformerEngine}
         if self.configs.use_model not in engines:
             raise Exception(f"masr_b200: model '{self.configs.use_model}' is not implemented yet "
                             f"(available: {sorted(engines)})")

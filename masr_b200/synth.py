@@ -135,6 +135,72 @@ def efficient_conformer_state_dict(seed: int = 0, vocab_size: int = DEFAULT_VOCA
     return sd
 
 
+def squeezeformer_state_dict(seed: int = 0, vocab_size: int = DEFAULT_VOCAB_SIZE, streaming: bool = True, input_dim: int = 80,
+                             d: int = 256, heads: int = 4, ffn: int = 2048, num_blocks: int = 12, kernel: int = 31,
+                             ctc_gain: float = 6.0, blank_bias: float = None) -> Dict[str, np.ndarray]:
+    """Squeezeformer tensors in the reference layout (configs/squeezeformer.yml; squeezeformer/encoder.py:20-166):
+    adaptive scale/bias per sub-module, BatchNorm running statistics in the conv module, the time-reduction
+    depthwise conv (kernel 1 when streaming, 5 otherwise) and the recover linear."""
+    rng = np.random.default_rng(900 + seed)
+    if blank_bias is None:
+        blank_bias = 10.6 if streaming else 8.6
+    dk = d // heads
+    sd: Dict[str, np.ndarray] = {}
+    mean, istd = cmvn_stats(seed, input_dim)
+    sd["encoder.global_cmvn.mean"] = mean
+    sd["encoder.global_cmvn.istd"] = istd
+    sd["encoder.embed.pw_conv.weight"] = _uniform(rng, (d, 1, 3, 3), 1.0 / 3.0)
+    sd["encoder.embed.pw_conv.bias"] = _uniform(rng, (d,), 1.0 / 3.0)
+    b2 = 1.0 / math.sqrt(d * 9)
+    sd["encoder.embed.dw_conv.weight"] = _uniform(rng, (d, d, 3, 3), b2)
+    sd["encoder.embed.dw_conv.bias"] = _uniform(rng, (d,), b2)
+    f2 = ((input_dim - 1) // 2 - 1) // 2
+    _linear(rng, sd, "encoder.embed.input_proj.0", d, d * f2, gain=1.0 / math.sqrt(d) * 2)   # input is pre-scaled by sqrt(d)
+    _layer_norm(rng, sd, "encoder.preln", d)
+
+    def ada(p):
+        sd[p + "ada_scale"] = (1.0 + 0.1 * rng.standard_normal((1, 1, d))).astype(np.float32)
+        sd[p + "ada_bias"] = (0.1 * rng.standard_normal((1, 1, d))).astype(np.float32)
+
+    for i in range(num_blocks):
+        p = f"encoder.encoders.{i}."
+        xav = math.sqrt(6.0 / (heads + dk))
+        sd[p + "self_attn.pos_bias_u"] = _uniform(rng, (heads, dk), xav)
+        sd[p + "self_attn.pos_bias_v"] = _uniform(rng, (heads, dk), xav)
+        ada(p + "self_attn.")
+        for nm in ("linear_q", "linear_k", "linear_v", "linear_out"):
+            _linear(rng, sd, p + "self_attn." + nm, d, d)
+        _linear(rng, sd, p + "self_attn.linear_pos", d, d, bias=False)
+        for ff in ("ffn1", "ffn2"):
+            ada(p + ff + ".")
+            _linear(rng, sd, p + ff + ".w_1", ffn, d)
+            _linear(rng, sd, p + ff + ".w_2", d, ffn)
+        c = p + "conv_module."
+        ada(c)
+        bpw = 1.0 / math.sqrt(d)
+        sd[c + "pointwise_conv1.weight"] = _uniform(rng, (2 * d, d, 1), bpw)
+        sd[c + "pointwise_conv1.bias"] = _uniform(rng, (2 * d,), bpw)
+        sd[c + "depthwise_conv.weight"] = _uniform(rng, (d, 1, kernel), 1.0 / math.sqrt(kernel))
+        sd[c + "depthwise_conv.bias"] = _uniform(rng, (d,), 1.0 / math.sqrt(kernel))
+        _layer_norm(rng, sd, c + "norm", d)                                     # BatchNorm affine
+        sd[c + "norm.running_mean"] = (0.05 * rng.standard_normal(d)).astype(np.float32)
+        sd[c + "norm.running_var"] = (0.1 + 0.05 * rng.uniform(0, 1, d)).astype(np.float32)
+        sd[c + "norm.num_batches_tracked"] = np.array(1000, np.int64)
+        sd[c + "pointwise_conv2.weight"] = _uniform(rng, (d, d, 1), bpw)
+        sd[c + "pointwise_conv2.bias"] = _uniform(rng, (d,), bpw)
+        for nm in ("layer_norm1", "layer_norm2", "layer_norm3", "layer_norm4"):
+            _layer_norm(rng, sd, p + nm, d)
+    kt = 1 if streaming else 5
+    sd["encoder.time_reduction_layer.dw_conv.weight"] = _uniform(rng, (d, 1, kt), 1.0 / math.sqrt(kt))
+    sd["encoder.time_reduction_layer.dw_conv.bias"] = _uniform(rng, (d,), 1.0 / math.sqrt(kt))
+    sd["encoder.time_reduction_layer.pw_conv.weight"] = _uniform(rng, (d, d, 1), 1.0 / math.sqrt(d))
+    sd["encoder.time_reduction_layer.pw_conv.bias"] = _uniform(rng, (d,), 1.0 / math.sqrt(d))
+    _linear(rng, sd, "encoder.time_recover_layer", d, d)
+    _linear(rng, sd, "ctc.ctc_lo", vocab_size, d, gain=ctc_gain)
+    sd["ctc.ctc_lo.bias"][0] += np.float32(blank_bias)
+    return sd
+
+
 def vocabulary(vocab_size: int = DEFAULT_VOCAB_SIZE) -> List[str]:
     """``<blank>``, ``<unk>``, CJK code points…, one ``<space>``, ``<eos>`` last — the order
     the reference's ``create_data`` writes (masr/trainer.py:480-488)."""
