@@ -191,6 +191,15 @@ int masr_grouped_attention_f32(const float* Q, const float* K, const float* V, c
 int masr_avgpool2_time_f32(const float* x, int64_t in_bstride, float* y, int64_t out_bstride, const int* lens, int B,
                            int out_rows, int D, void* stream);
 
+/* One time step of torch.nn.LSTM as DeepSpeech2 uses it (masr/model_utils/deepspeech2/encoder.py:36-45, packed ragged
+ * batches): gates_x [B*bstride, 4H] = W_ih x + b_ih + b_hh (gate order i,f,g,o); Whh [4H, H]; states transposed and
+ * batch-chunked h_*_T [ceil(B/32)][H][32] (ping-pong: in != out), c_state [B][H]; utterance b is active while
+ * step < lens[b] and uses time index step (forward) or lens[b]-1-step (reverse); h_t is written to
+ * out[(b*bstride + t), col_off + u] as fp32 and/or fp16 pair. */
+int masr_lstm_step_f32(const float* gates_x, int64_t ldg, int64_t bstride, const float* Whh, const float* h_in_T,
+                       float* h_out_T, float* c_state, float* out, void* outh, void* outl, int64_t ld_out, int col_off,
+                       const int* lens, int B, int H, int step, int reverse, void* stream);
+
 /* ---- CTC head / greedy decode ------------------------------------------------------------------- */
 
 /* softmax statistics of CTCLoss.softmax (masr/model_utils/loss/ctc.py:70) fused with the argmax of
@@ -204,6 +213,23 @@ int masr_ctc_frame_argmax_f32(const float* logits, int64_t ldl, int M, int V, in
  * psum/pcount = float32 left-to-right sum / count of maxp over non-blank frames (score = 100*psum/pcount). */
 int masr_ctc_greedy_collapse(const int* ids, const float* maxp, int64_t bstride, const int* lens, int B, int blank,
                              int* tokens, int64_t tok_stride, int* ntok, float* psum, int* pcount, void* stream);
+
+/* ---- CTC prefix beam search (no LM) --------------------------------------------------------------------
+ * Replaces the external paddlespeech_ctcdecoders call behind masr/decoders/swig_wrapper.py:35-64
+ * (`ctc_beam_search_decoding(probs, vocab, beam_size, cutoff_prob, cutoff_top_n, scorer, blank_id)`), scorer = None.
+ * PARITY UNPINNED (library absent): semantics per SURVEY.md Appendix D, checked against oracle/beam.py.
+ *  masr_ctc_topk_f32:     per frame the <= top_n (<= 40) most probable tokens, cut where the cumulative probability
+ *                         reaches cutoff_prob: cand_id / cand_logp [M, 40] (best first), cand_cnt [M];
+ *  masr_ctc_prefix_beam:  per utterance (rows b*bstride + t, t < lens[b]) the best prefix: out_tok [B, tok_stride],
+ *                         out_n [B], out_score [B] = log P(prefix); beam_size <= 512.  Scratch sizes from
+ *                         masr_ctc_prefix_beam_workspace (pool floats total, trie ints per utterance for each of
+ *                         trie_parent / trie_tok). */
+int masr_ctc_topk_f32(const float* logits, int64_t ldl, int M, int V, int top_n, float cutoff_prob, int* cand_id,
+                      float* cand_logp, int* cand_cnt, void* stream);
+int masr_ctc_prefix_beam_workspace(int B, int Tmax, int64_t* pool_floats_host, int64_t* trie_ints_per_utt_host);
+int masr_ctc_prefix_beam(const int* cand_id, const float* cand_logp, const int* cand_cnt, int64_t bstride, const int* lens,
+                         int B, int beam_size, int blank, float* pool, int* trie_parent, int* trie_tok, int64_t trie_cap,
+                         int* out_tok, int64_t tok_stride, int* out_n, float* out_score, void* stream);
 
 #ifdef __cplusplus
 }

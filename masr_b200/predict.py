@@ -101,13 +101,14 @@ class MASRPredictor:
         if not os.path.exists(model_path):
             raise Exception("模型文件不存在，请检查{}是否存在！".format(model_path))
         from .squeezeformer import SqueezeformerEngine
+        from .deepspeech2 import DeepSpeech2Engine
         engines = {'conformer': ConformerEngine, 'efficient_conformer': EfficientConformerEngine,
-                   'squeezeformer': SqueezeformerEngine}
+                   'squeezeformer': SqueezeformerEngine, 'deepspeech2': DeepSpeech2Engine}
         if self.configs.use_model not in engines:
             raise Exception(f"masr_b200: model '{self.configs.use_model}' is not implemented yet "
                             f"(available: {sorted(engines)})")
         self.predictor = engines[self.configs.use_model](model_path, streaming=bool(self.configs.streaming))
-        self._can_stream = self.configs.use_model == 'conformer'
+        self._can_stream = self.configs.use_model in ('conformer', 'deepspeech2')
         if self.predictor.V != self._text_featurizer.vocab_size:
             raise Exception(f"vocabulary has {self._text_featurizer.vocab_size} entries but the model's CTC head has "
                             f"{self.predictor.V}")

@@ -201,6 +201,38 @@ def squeezeformer_state_dict(seed: int = 0, vocab_size: int = DEFAULT_VOCAB_SIZE
     return sd
 
 
+def deepspeech2_state_dict(seed: int = 0, vocab_size: int = DEFAULT_VOCAB_SIZE, streaming: bool = True, input_dim: int = 80,
+                           layers: int = 5, hidden: int = 1024, ctc_gain: float = 4.0, blank_bias: float = 9.0) -> Dict[str, np.ndarray]:
+    """DeepSpeech2 tensors in the reference layout (deepspeech2/{conv,encoder,model}.py): Conv2d(1,32,3,2), Conv2d(32,32,3,2),
+    5 x LSTM(1024) (+ ``_reverse`` weights when not streaming) with LayerNorm, ``decoder.ctc_lo``."""
+    rng = np.random.default_rng(1300 + seed)
+    sd: Dict[str, np.ndarray] = {}
+    mean, istd = cmvn_stats(seed, input_dim)
+    sd["encoder.global_cmvn.mean"] = mean
+    sd["encoder.global_cmvn.istd"] = istd
+    sd["encoder.conv.conv.0.weight"] = _uniform(rng, (32, 1, 3, 3), 1.0 / 3.0)
+    sd["encoder.conv.conv.0.bias"] = _uniform(rng, (32,), 1.0 / 3.0)
+    b2 = 1.0 / math.sqrt(32 * 9)
+    sd["encoder.conv.conv.2.weight"] = _uniform(rng, (32, 32, 3, 3), b2)
+    sd["encoder.conv.conv.2.bias"] = _uniform(rng, (32,), b2)
+    f2 = ((input_dim - 1) // 2 - 1) // 2
+    dirs = 1 if streaming else 2
+    insz = 32 * f2
+    k = 1.0 / math.sqrt(hidden)
+    for l in range(layers):
+        p = f"encoder.rnns.{l}.rnn."
+        for suf in ("", "_reverse")[:dirs]:
+            sd[p + "weight_ih_l0" + suf] = _uniform(rng, (4 * hidden, insz), k)
+            sd[p + "weight_hh_l0" + suf] = _uniform(rng, (4 * hidden, hidden), k)
+            sd[p + "bias_ih_l0" + suf] = _uniform(rng, (4 * hidden,), k)
+            sd[p + "bias_hh_l0" + suf] = _uniform(rng, (4 * hidden,), k)
+        _layer_norm(rng, sd, f"encoder.rnns.{l}.layer_norm", hidden * dirs)
+        insz = hidden * dirs
+    _linear(rng, sd, "decoder.ctc_lo", vocab_size, hidden * dirs, gain=ctc_gain)
+    sd["decoder.ctc_lo.bias"][0] += np.float32(blank_bias)
+    return sd
+
+
 def vocabulary(vocab_size: int = DEFAULT_VOCAB_SIZE) -> List[str]:
     """``<blank>``, ``<unk>``, CJK code points…, one ``<space>``, ``<eos>`` last — the order
     the reference's ``create_data`` writes (masr/trainer.py:480-488)."""

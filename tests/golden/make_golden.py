@@ -55,6 +55,11 @@ SQUEEZE_CASES = [  # (name, streaming, weight seed, audio kind, audio seed, samp
     ("sqz_noncausal_speech_1p3s", False, 1, "speech", 26, 20800 + 37),
 ]
 
+DS2_CASES = [  # (name, streaming, weight seed, audio kind, audio seed, samples)
+    ("ds2_uni_speech_1p5s", True, 0, "speech", 35, 24000),
+    ("ds2_bi_speech_1p2s", False, 1, "speech", 36, 19200 + 80),
+]
+
 STREAM_CASE = ("stream_speech_3p4s", 0, "speech", 30, 54400, 8000)  # weight seed, kind, audio seed, samples, push
 
 
@@ -194,6 +199,39 @@ def gen_squeezeformer(tmp):
     np.savez_compressed(os.path.join(HERE, "squeezeformer_golden.npz"), **out)
 
 
+def gen_deepspeech2(tmp):
+    from masr.data_utils.audio import AudioSegment
+    from masr.data_utils.featurizer.audio_featurizer import AudioFeaturizer
+    from masr.decoders.ctc_greedy_decoder import greedy_decoder
+    from masr.model_utils.deepspeech2.model import DeepSpeech2Model
+    af = AudioFeaturizer(feature_method="fbank", n_mels=80, sample_rate=16000, use_dB_normalization=True, target_dB=-20)
+    cfg = yaml.safe_load(open(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "deepspeech2.yml"), encoding="utf-8"))
+    vocab = synth.vocabulary(V)
+    out, meta = {}, []
+    for name, streaming, wseed, kind, aseed, n in DS2_CASES:
+        mi = os.path.join(tmp, f"mean_istd_{wseed}.json")
+        synth.write_mean_istd(mi, wseed)
+        model = DeepSpeech2Model(input_dim=80, vocab_size=V, mean_istd_path=mi, streaming=streaming,
+                                 encoder_conf=cfg["encoder_conf"], decoder_conf=cfg["decoder_conf"])
+        res = model.load_state_dict(synth.to_torch(synth.deepspeech2_state_dict(wseed, V, streaming=streaming)), strict=True)
+        scripted = model.eval().export()
+        x = make_audio(kind, aseed, n)
+        feat = torch.from_numpy(af.featurize(AudioSegment.from_ndarray(x.copy(), 16000)))[None]
+        with torch.no_grad():
+            probs = scripted.get_encoder_out(feat, torch.tensor([feat.shape[1]]))[0]
+        score, text = greedy_decoder(probs.numpy(), vocab)
+        top = probs.topk(8, dim=1)
+        out[name + "/feat"] = feat[0].numpy()
+        out[name + "/top_p"] = top.values.numpy()
+        out[name + "/top_i"] = top.indices.numpy().astype(np.int32)
+        out[name + "/ids"] = probs.argmax(1).numpy().astype(np.int32)
+        meta.append({"name": name, "streaming": streaming, "wseed": wseed, "kind": kind, "aseed": aseed, "samples": n,
+                     "score": score, "text": text})
+        print(name, "T", probs.shape[0], "score", score, "text", text)
+    out["meta"] = np.frombuffer(json.dumps(meta, ensure_ascii=False).encode("utf-8"), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "deepspeech2_golden.npz"), **out)
+
+
 def gen_predictor(tmp):
     """The real ``MASRPredictor`` end to end (greedy): whole-utterance and streaming pushes."""
     from masr.predict import MASRPredictor
@@ -235,7 +273,9 @@ def gen_predictor(tmp):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     with tempfile.TemporaryDirectory() as tmp:
-        which = sys.argv[1:] or ["fbank", "encoder", "predictor", "efficient", "squeezeformer"]
+        which = sys.argv[1:] or ["fbank", "encoder", "predictor", "efficient", "squeezeformer", "deepspeech2"]
+        if "deepspeech2" in which:
+            gen_deepspeech2(tmp)
         if "squeezeformer" in which:
             gen_squeezeformer(tmp)
         if "fbank" in which:
