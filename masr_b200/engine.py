@@ -391,6 +391,52 @@ class ConformerEngine:
                 _p(ws["tokens"]), ws["tokens"].shape[1], _p(ws["ntok"]), _p(ws["psum"]), _p(ws["pcount"]))
         return probs
 
+    # ---- CTC prefix beam search (no LM) ----------------------------------------------------------
+    def ctc_beam(self, enc: torch.Tensor, out_lens: Sequence[int], T: int, ws, beam_size: int = 300,
+                 cutoff_prob: float = 0.99, cutoff_top_n: int = 40):
+        """`ctc_beam_search_decoding(probs, vocab, beam_size, cutoff_prob, cutoff_top_n, None, blank_id=0)` of the reference's
+        external decoder (masr/decoders/swig_wrapper.py:35-64) for a whole batch on the GPU -> device tensors
+        (tokens [B,T], count [B], log-score [B]).  Parity unpinned."""
+        B = len(out_lens)
+        M = B * T
+        dev = self.device
+        logits = self.ctc_logits(enc, ws)
+        if "cand_id" not in ws or ws["cand_id"].shape[0] < M:
+            ws["cand_id"] = torch.empty(M, 40, device=dev, dtype=torch.int32)
+            ws["cand_lp"] = torch.empty(M, 40, device=dev, dtype=torch.float32)
+            ws["cand_n"] = torch.empty(M, device=dev, dtype=torch.int32)
+            pool_n, trie_n = _lib.C.c_int64(0), _lib.C.c_int64(0)
+            call("masr_ctc_prefix_beam_workspace", B, T, _lib.C.byref(pool_n), _lib.C.byref(trie_n))
+            ws["beam_pool"] = torch.empty(pool_n.value, device=dev, dtype=torch.float32)
+            ws["trie_par"] = torch.empty(B * trie_n.value, device=dev, dtype=torch.int32)
+            ws["trie_tok"] = torch.empty(B * trie_n.value, device=dev, dtype=torch.int32)
+            ws["trie_cap"] = trie_n.value
+            ws["beam_tok"] = torch.zeros(B, max(1, T), device=dev, dtype=torch.int32)
+            ws["beam_n"] = torch.zeros(B, device=dev, dtype=torch.int32)
+            ws["beam_score"] = torch.zeros(B, device=dev, dtype=torch.float32)
+        self._k("ctc_topk", "masr_ctc_topk_f32", _p(logits), self.Vpad, M, self.V, int(cutoff_top_n), float(cutoff_prob),
+                _p(ws["cand_id"]), _p(ws["cand_lp"]), _p(ws["cand_n"]))
+        self._k("prefix_beam", "masr_ctc_prefix_beam", _p(ws["cand_id"]), _p(ws["cand_lp"]), _p(ws["cand_n"]), T, _p(ws["tlens"]),
+                B, int(beam_size), 0, _p(ws["beam_pool"]), _p(ws["trie_par"]), _p(ws["trie_tok"]), ws["trie_cap"],
+                _p(ws["beam_tok"]), ws["beam_tok"].shape[1], _p(ws["beam_n"]), _p(ws["beam_score"]))
+        return ws["beam_tok"], ws["beam_n"], ws["beam_score"]
+
+    def transcribe_beam(self, waves: Sequence[np.ndarray], beam_size: int = 300, cutoff_prob: float = 0.99,
+                        cutoff_top_n: int = 40, use_db_normalization: bool = True, target_db: float = -20.0):
+        """Host waveforms -> (token ids per utterance, log-scores) with the GPU prefix beam search."""
+        feats, frames, status = self.fbank(waves, use_db_normalization, target_db)
+        return self.beam_features(feats, frames, beam_size, cutoff_prob, cutoff_top_n)
+
+    def beam_features(self, feats, frames, beam_size: int = 300, cutoff_prob: float = 0.99, cutoff_top_n: int = 40):
+        B = feats.shape[0]
+        enc, tl, T, ws = self.encode(feats, frames)
+        if T == 0:
+            return [[] for _ in range(B)], [0.0] * B
+        tok, n, sc = self.ctc_beam(enc, tl, T, ws, beam_size, cutoff_prob, cutoff_top_n)
+        tok, n, sc = tok.cpu().numpy(), n.cpu().numpy(), sc.cpu().numpy()
+        self.d2h_bytes += tok.nbytes + n.nbytes + sc.nbytes
+        return [tok[b, :n[b]].tolist() for b in range(B)], [float(s) for s in sc]
+
     # ---- public batched entry points -----------------------------------------------------------
     def transcribe(self, waves: Sequence[np.ndarray], use_db_normalization: bool = True, target_db: float = -20.0,
                    return_frames: bool = False) -> GreedyResult:

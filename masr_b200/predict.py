@@ -94,10 +94,14 @@ class MASRPredictor:
         self._sample_rate = int(pc.get('sample_rate', 16000))
         self._use_db = bool(pc.get('use_dB_normalization', True))
         self._target_db = float(pc.get('target_dB', -20))
+        self._beam_conf = None
         if self.configs.decoder == 'ctc_beam_search':
-            # the reference falls back to greedy when its external C++ decoder is missing (predict.py:103-109)
-            logger.warning('ctc_beam_search is not wired into MASRPredictor yet; using ctc_greedy')
-            self.configs.decoder = 'ctc_greedy'
+            # GPU prefix beam search without a language model (the reference's external decoder + KenLM file are not
+            # available; alpha/beta/language_model_path are ignored).  Whole-utterance calls only; streaming stays greedy.
+            bc = dict(self.configs.get('ctc_beam_search_decoder_conf', {}) or {})
+            self._beam_conf = {'beam_size': int(bc.get('beam_size', 300)), 'cutoff_prob': float(bc.get('cutoff_prob', 0.99)),
+                               'cutoff_top_n': int(bc.get('cutoff_top_n', 40))}
+            logger.warning('ctc_beam_search: GPU prefix beam search without LM (alpha/beta ignored)')
         if not os.path.exists(model_path):
             raise Exception("模型文件不存在，请检查{}是否存在！".format(model_path))
         from .squeezeformer import SqueezeformerEngine
@@ -140,6 +144,11 @@ class MASRPredictor:
         """Whole-utterance recognition (predict.py:167-192)."""
         samples, sr = load_audio(audio_data, sample_rate)
         self._check_rate(sr)
+        if self._beam_conf is not None:
+            toks, scores = self.predictor.transcribe_beam([samples], use_db_normalization=self._use_db,
+                                                          target_db=self._target_db, **self._beam_conf)
+            text = ids_to_text(toks[0], self._text_featurizer.vocab_list)
+            return {'text': self._finish(text, use_pun, is_itn), 'score': scores[0]}
         res = self.predictor.transcribe([samples], self._use_db, self._target_db)
         self._raise_status(res.status)
         text = ids_to_text(res.tokens[0], self._text_featurizer.vocab_list)
@@ -152,6 +161,11 @@ class MASRPredictor:
             s, sr = load_audio(a, sample_rate)
             self._check_rate(sr)
             waves.append(s)
+        if self._beam_conf is not None:
+            toks, scores = self.predictor.transcribe_beam(waves, use_db_normalization=self._use_db,
+                                                          target_db=self._target_db, **self._beam_conf)
+            vocab = self._text_featurizer.vocab_list
+            return [{'text': ids_to_text(t, vocab), 'score': s} for t, s in zip(toks, scores)]
         res = self.predictor.transcribe(waves, self._use_db, self._target_db)
         self._raise_status(res.status)
         vocab = self._text_featurizer.vocab_list

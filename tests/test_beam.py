@@ -1,0 +1,99 @@
+"""CTC prefix beam search (no LM; parity unpinned — the reference's external decoder is absent): the CPU restatement is
+checked against its defining properties, and the CUDA kernels against the restatement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import beam as obeam, ctc as octc
+
+
+def rand_posteriors(seed, T, V, peaky=6.0, blank_boost=2.0):
+    rng = np.random.default_rng(seed)
+    logits = rng.standard_normal((T, V)).astype(np.float32) * peaky
+    logits[:, 0] += blank_boost
+    # temporal smoothness so repeats occur
+    for t in range(1, T):
+        logits[t] = 0.5 * logits[t] + 0.5 * logits[t - 1]
+    e = np.exp(logits - logits.max(1, keepdims=True))
+    return (e / e.sum(1, keepdims=True)).astype(np.float32), logits
+
+
+def test_pruning_rule():
+    p = np.array([0.05, 0.5, 0.3, 0.1, 0.05], np.float32)
+    assert [c for c, _ in obeam.prune_frame(p, 0.99, 40)] == [1, 2, 3, 0, 4]
+    assert [c for c, _ in obeam.prune_frame(p, 0.85, 40)] == [1, 2, 3]
+    assert [c for c, _ in obeam.prune_frame(p, 0.99, 2)] == [1, 2]
+    assert [c for c, _ in obeam.prune_frame(np.array([0.25, 0.25, 0.25, 0.25], np.float32), 0.5, 40)] == [0, 1]   # ties: lower id first
+
+
+def test_beam1_on_one_hot_equals_greedy():
+    rng = np.random.default_rng(0)
+    T, V = 40, 50
+    ids = rng.integers(0, 6, T)
+    probs = np.full((T, V), 1e-9, np.float32)
+    probs[np.arange(T), ids] = 1.0
+    (score, toks), = obeam.prefix_beam_search(probs, beam_size=1, cutoff_prob=1.0, cutoff_top_n=V)
+    assert toks == octc.collapse(ids)
+    assert abs(score) < 1e-4
+
+
+def test_wider_beam_never_scores_worse_and_sums_paths():
+    probs, _ = rand_posteriors(1, 25, 30)
+    s1 = obeam.prefix_beam_search(probs, beam_size=1, cutoff_prob=1.0, cutoff_top_n=30)[0][0]
+    s8 = obeam.prefix_beam_search(probs, beam_size=8, cutoff_prob=1.0, cutoff_top_n=30)[0][0]
+    s64 = obeam.prefix_beam_search(probs, beam_size=64, cutoff_prob=1.0, cutoff_top_n=30)[0][0]
+    assert s8 >= s1 - 1e-5 and s64 >= s8 - 1e-5
+    # exact check on a tiny case: the prefix probability is the sum over all alignments that collapse to it
+    T, V = 4, 3
+    p, _ = rand_posteriors(2, T, V, peaky=1.0, blank_boost=0.0)
+    import itertools
+    mass = {}
+    for path in itertools.product(range(V), repeat=T):
+        key = tuple(octc.collapse(path))
+        mass[key] = mass.get(key, 0.0) + float(np.prod([p[t, c] for t, c in enumerate(path)]))
+    best = max(mass.items(), key=lambda kv: kv[1])
+    (score, toks), = obeam.prefix_beam_search(p, beam_size=50, cutoff_prob=1.0, cutoff_top_n=V)
+    assert tuple(toks) == best[0] and abs(np.exp(score) - best[1]) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,T,beam,topn,cut", [(3, 60, 300, 40, 0.99), (4, 37, 16, 40, 0.99), (5, 80, 300, 10, 1.0), (6, 25, 1, 40, 0.99)])
+def test_gpu_beam_equals_restatement(seed, T, beam, topn, cut):
+    from masr_b200 import _lib
+    _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    V = 4233
+    probs, logits = rand_posteriors(seed, T, V)
+    lens = [T, max(1, T // 2)]
+    B = len(lens)
+    ldl = (V + 15) // 16 * 16
+    L = torch.zeros(B * T, ldl, device=dev)
+    L[:T, :V] = torch.from_numpy(logits).to(dev)
+    L[T:2 * T, :V] = torch.from_numpy(logits[::-1].copy()).to(dev)          # second utterance: the reversed sequence
+    st = torch.cuda.current_stream().cuda_stream
+    cid = torch.empty(B * T, 40, dtype=torch.int32, device=dev); clp = torch.empty(B * T, 40, device=dev)
+    cn = torch.empty(B * T, dtype=torch.int32, device=dev)
+    _lib.call("masr_ctc_topk_f32", L.data_ptr(), ldl, B * T, V, topn, cut, cid.data_ptr(), clp.data_ptr(), cn.data_ptr(), st)
+    # candidate lists equal the restatement's pruning
+    ph = torch.softmax(L[:, :V], 1).cpu().numpy()
+    cid_h, cn_h = cid.cpu().numpy(), cn.cpu().numpy()
+    for r in (0, T // 2, T - 1, T + 3):
+        want = [c for c, _ in obeam.prune_frame(ph[r], cut, topn)]
+        assert cid_h[r, :cn_h[r]].tolist() == want
+    import ctypes as C
+    pool_n, trie_n = C.c_int64(0), C.c_int64(0)
+    _lib.call("masr_ctc_prefix_beam_workspace", B, T, C.byref(pool_n), C.byref(trie_n))
+    pool = torch.empty(pool_n.value, device=dev); tp = torch.empty(B * trie_n.value, dtype=torch.int32, device=dev)
+    tt = torch.empty_like(tp)
+    ld = torch.tensor(lens, dtype=torch.int32, device=dev)
+    otok = torch.zeros(B, T, dtype=torch.int32, device=dev); on = torch.zeros(B, dtype=torch.int32, device=dev)
+    osc = torch.zeros(B, device=dev)
+    _lib.call("masr_ctc_prefix_beam", cid.data_ptr(), clp.data_ptr(), cn.data_ptr(), T, ld.data_ptr(), B, beam, 0, pool.data_ptr(),
+              tp.data_ptr(), tt.data_ptr(), trie_n.value, otok.data_ptr(), T, on.data_ptr(), osc.data_ptr(), st)
+    torch.cuda.synchronize()
+    for b in range(B):
+        p = ph[b * T: b * T + lens[b]]
+        (score, toks), = obeam.prefix_beam_search(p, beam_size=beam, cutoff_prob=cut, cutoff_top_n=topn)
+        got = otok[b, :on[b].item()].cpu().tolist()
+        assert got == toks, (b, got, toks)
+        assert abs(osc[b].item() - score) < 2e-3 * max(1.0, abs(score))
