@@ -170,8 +170,11 @@ def main():
     if args.warmup < 3:
         args.warmup = 3                      # timing rule: W >= 3
 
+    import faulthandler
     import torch.distributed as dist
     from masr_b200 import build as _b, synth
+    # a hung collective must not eat the GPU budget: dump every thread's stack and exit if the run stalls
+    faulthandler.dump_traceback_later(int(os.environ.get("MASR_BENCH_WATCHDOG_S", "420")), exit=True)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -213,11 +216,11 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     T = 248
-    gather_buf = [torch.empty(BATCH_PER_GPU, T + 2, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+    gather_state = {}
 
     resident = eng.prepare_resident(waves) if eng.use_graphs else None
 
-    def device_step(eager=False):
+    def device_step(eager=False, gather=True):
         """One pass of the hot path with inputs resident in HBM: fbank -> encoder -> CTC greedy
         (+ the token gather across ranks).  Replayed as one CUDA graph; `eager` = the same kernels launched one
         by one (used for the per-kernel event timing of the roofline leg)."""
@@ -227,9 +230,12 @@ def main():
             feats, frames, status = eng.fbank(None, True, -20.0, wave_dev=wave_dev, offsets_dev=offs, lengths=lengths)
             enc, tl, Tm, ws = eng.encode(feats, frames)
             eng.ctc_greedy(enc, tl, Tm, ws)
-        if world > 1:
+        if world > 1 and gather:
+            # the only collective of the path: gather token ids + counters of every rank's shard (NCCL over NVLink)
             packed = torch.cat([ws["tokens"], ws["ntok"][:, None], ws["pcount"][:, None]], dim=1)
-            dist.all_gather(gather_buf, packed)
+            if "buf" not in gather_state or gather_state["buf"][0].shape != packed.shape:
+                gather_state["buf"] = [torch.empty_like(packed) for _ in range(world)]
+            dist.all_gather(gather_state["buf"], packed)
         return ws
 
     for _ in range(args.warmup):
@@ -288,7 +294,7 @@ def main():
         eng.profile(True)
         for _ in range(2):
             flush.zero_()
-            device_step(eager=True)
+            device_step(eager=True, gather=False)      # rank-0-only leg: no collective here
         torch.cuda.synchronize(dev)
         summ = eng.profile_summary()
         eng.profile(False)

@@ -156,12 +156,15 @@ int masr_relpos_attention_f32(const float* Q, int64_t ldq, int64_t q_bstride, co
                               const float* pos_v, float* O, void* Oh, void* Ol, int64_t ldo, int64_t o_bstride,
                               const int* q_lens, const int* k_lens, int B, int H, int d_k, int max_q, void* stream);
 
-/* Same contract as masr_relpos_attention_f32, computed on the tensor cores (mma.sync m16n8k16) with the
- * FP16x2 operand split (fp32-grade results); used by the batched path. */
-int masr_relpos_attention_tc(const float* Q, int64_t ldq, int64_t q_bstride, const float* K, const float* V,
-                             int64_t ldk, int64_t k_bstride, const float* P, int64_t ldp, const float* pos_u,
-                             const float* pos_v, float* O, void* Oh, void* Ol, int64_t ldo, int64_t o_bstride,
-                             const int* q_lens, const int* k_lens, int B, int H, int d_k, int max_q, void* stream);
+/* Same result as masr_relpos_attention_f32, computed on the tensor cores (mma.sync m16n8k16) with the FP16x2 operand
+ * split (fp32-grade); used by the batched path.  Q is fp32 (the positional biases are added before the split); K, V
+ * (row stride ldk halves, head h at column h*d_k) and P = linear_pos(pe) (ldp) arrive as fp16 (h,l) pairs — the qkv
+ * GEMM epilogue and the weight loader produce them — so key tiles are 16-byte cp.async copies. */
+int masr_relpos_attention_tc(const float* Q, int64_t ldq, int64_t q_bstride, const void* Kh, const void* Kl, const void* Vh,
+                             const void* Vl, int64_t ldk, int64_t k_bstride, const void* Ph, const void* Pl, int64_t ldp,
+                             const float* pos_u, const float* pos_v, float* O, void* Oh, void* Ol, int64_t ldo,
+                             int64_t o_bstride, const int* q_lens, const int* k_lens, int B, int H, int d_k, int max_q,
+                             void* stream);
 
 /* ConvolutionModule middle (masr/model_utils/conformer/convolution.py:121-126): depthwise Conv1d(k)
  * -> LayerNorm(C) -> SiLU.  y[b,t,:] for t < out_rows from g[b, t - lpad + k, :], k < kernel_size;

@@ -41,8 +41,8 @@ SIGNATURES = {
     "masr_upsample2_add_f32": [_vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp],
     "masr_relpos_attention_f32": [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                   _vp, _vp, _i, _i, _i, _i, _vp],
-    "masr_relpos_attention_tc": [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
-                                 _vp, _vp, _i, _i, _i, _i, _vp],
+    "masr_relpos_attention_tc": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
+                                 _i64, _vp, _vp, _i, _i, _i, _i, _vp],
     "masr_dwconv_ln_silu_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i,
                                 _i, _f, _vp],
     "masr_dwconv_ln_silu_strided_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i,

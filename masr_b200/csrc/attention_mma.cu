@@ -5,11 +5,12 @@
 //   out    = softmax_j(S[:, j < klen]) . v
 //   x.y   ~= xh.yh + 2^-11 (xh.yl + xl.yh),   h = fp16(x), l = fp16((x-h) 2^11)   -> fp32-grade results
 //
-// Same contract as relpos_attention_kernel (attention.cu), which stays as the fp32 FMA reference
-// implementation (used by the single-stream chunk path).  One CTA = 64 queries of one (utterance, head),
-// 4 warps x 16 query rows; keys stream through shared memory in tiles of 32; the score tile, the
-// probabilities and the output accumulators never leave registers (the S accumulator fragment of two
-// 8-key blocks is exactly the A fragment of the P.V MMA).
+// Same result contract as relpos_attention_kernel (attention.cu, the fp32 FMA reference used by the single-stream
+// chunk path), but K, V and linear_pos(pe) arrive already split into fp16 (h,l) pairs (the qkv GEMM's epilogue and
+// the weight loader write them), so key tiles are plain 16-byte cp.async copies, double-buffered against the MMAs.
+// One CTA = 64 queries of one (utterance, head), 4 warps x 16 query rows; keys stream in tiles of 32; the score tile,
+// the probabilities and the output accumulators never leave registers (the S accumulator fragment of two 8-key
+// blocks is exactly the A fragment of the P.V MMA).
 //
 // Round-1 note: this is the legacy HMMA path (a 5 % FLOP share of the step); the tcgen05 version is future work.
 #include <cuda_fp16.h>
@@ -27,9 +28,9 @@ constexpr int V_STRIDE = 72;    // halves per row of a [*, 64] tile
 constexpr float kLo = 2048.0f, kLoI = 1.0f / 2048.0f;
 
 struct AttnMmaParams {
-    const float* Q; int64_t ldq, q_bstride;
-    const float* K; const float* V; int64_t ldk, k_bstride;
-    const float* P; int64_t ldp;
+    const float* Q; int64_t ldq, q_bstride;                 // fp32 queries (the positional biases are added in fp32)
+    const __half* Kh; const __half* Kl; const __half* Vh; const __half* Vl; int64_t ldk, k_bstride;   // fp16 (h,l) pairs
+    const __half* Ph; const __half* Pl; int64_t ldp;        // linear_pos(pe) as fp16 pairs
     const float* pos_u; const float* pos_v;
     float* O; __half* Oh; __half* Ol; int64_t ldo, o_bstride;
     const int* q_lens; const int* k_lens;
@@ -53,6 +54,14 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills (rows beyond the key length)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // split 4 floats and store the h / l halves at dst_h / dst_l (8-byte aligned)
 __device__ __forceinline__ void split_store4(float4 v, __half* dst_h, __half* dst_l) {
@@ -64,16 +73,16 @@ __device__ __forceinline__ void split_store4(float4 v, __half* dst_h, __half* ds
     *reinterpret_cast<uint2*>(dst_l) = make_uint2(pack_h2(l0), pack_h2(l1));
 }
 
+constexpr int KT_HALVES = MKT * KC_STRIDE;     // one [32][136] operand tile
+constexpr int VT_HALVES = MKT * V_STRIDE;      // one [32][72]  operand tile
+constexpr int STAGE_HALVES = 2 * KT_HALVES + 2 * VT_HALVES;      // Kh|Ph, Kl|Pl, Vh, Vl
+constexpr size_t kAttnMmaSmem = (size_t)(2 * MQ * KC_STRIDE + 2 * STAGE_HALVES) * sizeof(__half);
+
 __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams p) {
-    // region A: Q tile [64][136] h + l (34816 B), later the K|P tile [32][136] h + l; region B: V tile [32][72] h + l
-    __shared__ __align__(16) __half sA[2 * MQ * KC_STRIDE];
-    __shared__ __align__(16) __half sV[2 * MKT * V_STRIDE];
-    __half* sQh = sA;
-    __half* sQl = sA + MQ * KC_STRIDE;
-    __half* sKh = sA;
-    __half* sKl = sA + MKT * KC_STRIDE;
-    __half* sVh = sV;
-    __half* sVl = sV + MKT * V_STRIDE;
+    extern __shared__ __align__(16) __half sm_att[];
+    __half* sQh = sm_att;                                   // [64][136]: [q+u | q+v] high parts
+    __half* sQl = sQh + MQ * KC_STRIDE;                     // low parts
+    __half* stage0 = sQl + MQ * KC_STRIDE;
 
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MQ;
     const int qlen = p.q_lens[b], klen = p.k_lens[b];
@@ -95,8 +104,36 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
         return;
     }
     const int nq = min(MQ, qlen - q0);
+    const int64_t krow0 = (int64_t)b * p.k_bstride;
+    const int ntiles = (klen + MKT - 1) / MKT;
 
-    // ---- stage [q+u | q+v] as fp16 pairs, then lift this warp's 16 rows into A fragments ----
+    // async stage of key tile `kt`: [k | p] (h,l) and v (h,l), 16-byte chunks, zero-filled beyond klen
+    auto load_tile = [&](int kt, int buf) {
+        __half* st = stage0 + buf * STAGE_HALVES;
+        const int k0 = kt * MKT;
+        for (int idx = tid; idx < MKT * 16 * 2; idx += 128) {          // K|P: 32 rows x 16 chunks x {h,l}
+            const int hl = idx >= MKT * 16, j = idx - hl * MKT * 16;
+            const int r = j >> 4, c = j & 15;                           // chunk c: 0-7 -> k dims, 8-15 -> p dims
+            const int key = k0 + r;
+            const bool ok = key < klen;
+            const int kr = ok ? key : 0;
+            const __half* src = c < 8 ? (hl ? p.Kl : p.Kh) + (krow0 + kr) * p.ldk + h * MD + c * 8
+                                      : (hl ? p.Pl : p.Ph) + (int64_t)kr * p.ldp + h * MD + (c - 8) * 8;
+            cp_async16(st + hl * KT_HALVES + r * KC_STRIDE + c * 8, src, ok ? 16 : 0);
+        }
+        for (int idx = tid; idx < MKT * 8 * 2; idx += 128) {           // V: 32 rows x 8 chunks x {h,l}
+            const int hl = idx >= MKT * 8, j = idx - hl * MKT * 8;
+            const int r = j >> 3, c = j & 7;
+            const int key = k0 + r;
+            const bool ok = key < klen;
+            const __half* src = (hl ? p.Vl : p.Vh) + (krow0 + (ok ? key : 0)) * p.ldk + h * MD + c * 8;
+            cp_async16(st + 2 * KT_HALVES + hl * VT_HALVES + r * V_STRIDE + c * 8, src, ok ? 16 : 0);
+        }
+    };
+    load_tile(0, 0);
+    cp_async_commit();
+
+    // ---- stage [q+u | q+v] as fp16 pairs (fp32 add first) ----
     {
         const float* qsrc = p.Q + ((int64_t)b * p.q_bstride + q0) * p.ldq + h * MD;
         for (int idx = tid; idx < MQ * 16; idx += 128) {
@@ -112,17 +149,6 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
             split_store4(qv, sQh + r * KC_STRIDE + MD + c, sQl + r * KC_STRIDE + MD + c);
         }
     }
-    __syncthreads();
-    uint32_t qh[8][4], ql[8][4];
-    {
-        const int row = warp * 16 + (lane & 15), colb = (lane >> 4) * 8;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-            ldsm_x4(qh[ks], sQh + row * KC_STRIDE + ks * 16 + colb);
-            ldsm_x4(ql[ks], sQl + row * KC_STRIDE + ks * 16 + colb);
-        }
-    }
-    __syncthreads();                            // region A is reused for the K|P tiles from here on
 
     float om[8][4], oc[8][4];
 #pragma unroll
@@ -130,30 +156,19 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
 #pragma unroll
         for (int j = 0; j < 4; ++j) { om[i][j] = 0.f; oc[i][j] = 0.f; }
     float m_row[2] = {-INFINITY, -INFINITY}, l_row[2] = {0.f, 0.f};
+    const int qrow = warp * 16 + (lane & 15), qcol = (lane >> 4) * 8;
 
-    const float* kbase = p.K + (int64_t)b * p.k_bstride * p.ldk + h * MD;
-    const float* vbase = p.V + (int64_t)b * p.k_bstride * p.ldk + h * MD;
-    const float* pbase = p.P + h * MD;
-
-    for (int k0 = 0; k0 < klen; k0 += MKT) {
-        const int nk = min(MKT, klen - k0);
-        // ---- stage the key tile: [k | p] -> sK, v -> sV (fp16 pairs) ----
-        for (int idx = tid; idx < MKT * 32; idx += 128) {
-            const int r = idx >> 5, cc = idx & 31;            // 32 float4 per row: 16 of k, 16 of p
-            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nk) {
-                v4 = cc < 16 ? ldg_f4(kbase + (int64_t)(k0 + r) * p.ldk + cc * 4)
-                             : ldg_f4(pbase + (int64_t)(k0 + r) * p.ldp + (cc - 16) * 4);
-            }
-            split_store4(v4, sKh + r * KC_STRIDE + cc * 4, sKl + r * KC_STRIDE + cc * 4);
-        }
-        for (int idx = tid; idx < MKT * 16; idx += 128) {
-            const int r = idx >> 4, c = (idx & 15) * 4;
-            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nk) v4 = ldg_f4(vbase + (int64_t)(k0 + r) * p.ldk + c);
-            split_store4(v4, sVh + r * V_STRIDE + c, sVl + r * V_STRIDE + c);
-        }
-        __syncthreads();
+    for (int kt = 0; kt < ntiles; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < ntiles) load_tile(kt + 1, buf ^ 1);     // prefetch the next tile into the other buffer
+        cp_async_commit();
+        cp_async_wait<1>();                                  // tile kt has landed (this thread's copies)
+        __syncthreads();                                     // ... and everyone's; also publishes the Q tile on kt == 0
+        const __half* sKh = stage0 + buf * STAGE_HALVES;
+        const __half* sKl = sKh + KT_HALVES;
+        const __half* sVh = sKh + 2 * KT_HALVES;
+        const __half* sVl = sVh + VT_HALVES;
+        const int nk = min(MKT, klen - kt * MKT);
 
         // ---- S = Qcat . Kcat^T (3 MMAs per k-step per 8-key block) ----
         float sm[4][4], sc[4][4];
@@ -162,21 +177,23 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
 #pragma unroll
             for (int j = 0; j < 4; ++j) { sm[i][j] = 0.f; sc[i][j] = 0.f; }
         {
-            // ldmatrix.x4: matrices (keys 0-7,dims 0-7), (keys 0-7,dims 8-15), (keys 8-15,dims 0-7), (keys 8-15,dims 8-15)
             const int key = (lane >> 4) * 8 + (lane & 7), dim = ((lane >> 3) & 1) * 8;
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
+                uint32_t qh[4], ql[4];
+                ldsm_x4(qh, sQh + qrow * KC_STRIDE + ks * 16 + qcol);
+                ldsm_x4(ql, sQl + qrow * KC_STRIDE + ks * 16 + qcol);
 #pragma unroll
                 for (int np = 0; np < 2; ++np) {               // pairs of 8-key blocks
                     uint32_t kh4[4], kl4[4];
                     ldsm_x4(kh4, sKh + (np * 16 + key) * KC_STRIDE + ks * 16 + dim);
                     ldsm_x4(kl4, sKl + (np * 16 + key) * KC_STRIDE + ks * 16 + dim);
-                    mma16816(sm[2 * np], qh[ks], kh4[0], kh4[1]);
-                    mma16816(sc[2 * np], qh[ks], kl4[0], kl4[1]);
-                    mma16816(sc[2 * np], ql[ks], kh4[0], kh4[1]);
-                    mma16816(sm[2 * np + 1], qh[ks], kh4[2], kh4[3]);
-                    mma16816(sc[2 * np + 1], qh[ks], kl4[2], kl4[3]);
-                    mma16816(sc[2 * np + 1], ql[ks], kh4[2], kh4[3]);
+                    mma16816(sm[2 * np], qh, kh4[0], kh4[1]);
+                    mma16816(sc[2 * np], qh, kl4[0], kl4[1]);
+                    mma16816(sc[2 * np], ql, kh4[0], kh4[1]);
+                    mma16816(sm[2 * np + 1], qh, kh4[2], kh4[3]);
+                    mma16816(sc[2 * np + 1], qh, kl4[2], kl4[3]);
+                    mma16816(sc[2 * np + 1], ql, kh4[2], kh4[3]);
                 }
             }
         }
@@ -210,7 +227,6 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
                 pv[j] = expf(sm[nb][j] - m_row[j >> 1]);
                 rs[j >> 1] += pv[j];
             }
-            // S fragment (rows g / g+8, keys nb*8 + 2t, +1) -> A fragment of k-step nb/2, halves (nb&1)
             const __half2 h01 = __floats2half2_rn(pv[0], pv[1]), h23 = __floats2half2_rn(pv[2], pv[3]);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const __half2 l01 = __floats2half2_rn((pv[0] - f01.x) * kLo, (pv[1] - f01.y) * kLo);
@@ -228,7 +244,6 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
         }
         // ---- O += P . V ----
         {
-            // ldmatrix.x4.trans on V[key][d]: matrices (keys 0-7,d 0-7), (keys 8-15,d 0-7), (keys 0-7,d 8-15), (keys 8-15,d 8-15)
             const int key = ((lane >> 3) & 1) * 8 + (lane & 7), dcol = (lane >> 4) * 8;
 #pragma unroll
             for (int j2 = 0; j2 < 2; ++j2) {
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
                 }
             }
         }
-        __syncthreads();                        // tile consumed before the next one overwrites it
+        __syncthreads();                        // all warps done with `buf` before the next prefetch overwrites it
     }
 
     // ---- normalise and store (rows g, g+8; columns db*8 + 2t, +1) ----
@@ -281,19 +296,33 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
 
 using namespace masr;
 
-extern "C" int masr_relpos_attention_tc(const float* Q, int64_t ldq, int64_t q_bstride, const float* K, const float* V,
-                                        int64_t ldk, int64_t k_bstride, const float* P, int64_t ldp, const float* pos_u,
-                                        const float* pos_v, float* O, void* Oh, void* Ol, int64_t ldo, int64_t o_bstride,
-                                        const int* q_lens, const int* k_lens, int B, int H, int d_k, int max_q,
-                                        void* stream) {
+extern "C" int masr_relpos_attention_tc(const float* Q, int64_t ldq, int64_t q_bstride, const void* Kh, const void* Kl,
+                                        const void* Vh, const void* Vl, int64_t ldk, int64_t k_bstride, const void* Ph,
+                                        const void* Pl, int64_t ldp, const float* pos_u, const float* pos_v, float* O, void* Oh,
+                                        void* Ol, int64_t ldo, int64_t o_bstride, const int* q_lens, const int* k_lens, int B,
+                                        int H, int d_k, int max_q, void* stream) {
     if (B == 0 || max_q == 0) return MASR_OK;
-    MASR_REQUIRE(Q && K && V && P && pos_u && pos_v && (O || (Oh && Ol)) && q_lens && k_lens, "masr_relpos_attention_tc: null pointer");
+    MASR_REQUIRE(Q && Kh && Kl && Vh && Vl && Ph && Pl && pos_u && pos_v && (O || (Oh && Ol)) && q_lens && k_lens,
+                 "masr_relpos_attention_tc: null pointer");
     MASR_REQUIRE(d_k == MD, "masr_relpos_attention_tc: d_k=%d unsupported (this build: 64)", d_k);
-    MASR_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0,
-                 "masr_relpos_attention_tc: leading dimensions must be multiples of 4");
-    AttnMmaParams p{Q, ldq, q_bstride, K, V, ldk, k_bstride, P, ldp, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, ldo, o_bstride,
-                    q_lens, k_lens, 1.0f / sqrtf((float)d_k), max_q};
+    MASR_REQUIRE(ldq % 4 == 0 && ldk % 8 == 0 && ldp % 8 == 0 && ldo % 4 == 0,
+                 "masr_relpos_attention_tc: leading dimensions (ldq,ldo %% 4; ldk,ldp %% 8) misaligned");
+    MASR_REQUIRE(((reinterpret_cast<uintptr_t>(Kh) | reinterpret_cast<uintptr_t>(Kl) | reinterpret_cast<uintptr_t>(Vh) |
+                   reinterpret_cast<uintptr_t>(Vl) | reinterpret_cast<uintptr_t>(Ph) | reinterpret_cast<uintptr_t>(Pl)) & 15) == 0,
+                 "masr_relpos_attention_tc: K/V/P pair pointers must be 16-byte aligned");
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(relpos_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnMmaSmem);
+        if (e != cudaSuccess) { set_last_error("attention_mma smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set[dev] = true;
+    }
+    AttnMmaParams p{Q, ldq, q_bstride, (const __half*)Kh, (const __half*)Kl, (const __half*)Vh, (const __half*)Vl, ldk, k_bstride,
+                    (const __half*)Ph, (const __half*)Pl, ldp, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, ldo, o_bstride, q_lens,
+                    k_lens, 1.0f / sqrtf((float)d_k), max_q};
     dim3 grid((max_q + MQ - 1) / MQ, H, B);
-    relpos_attention_mma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    relpos_attention_mma_kernel<<<grid, 128, kAttnMmaSmem, (cudaStream_t)stream>>>(p);
     return check_launch("relpos_attention_mma_kernel");
 }

@@ -116,6 +116,21 @@ class ConformerEngine:
             t[i, "ff1"] = self._split(L.ff[0]); t[i, "ff2"] = self._split(L.ff[2])
         torch.cuda.synchronize(self.device)
 
+    def _ptab_pair(self, L):
+        """fp16 (h,l) pair of a layer's linear_pos(pe) table (cached on the layer object)."""
+        if getattr(L, "ptab_p", None) is None or L.ptab_p[2] is not L.ptab:
+            h, l = self._split(L.ptab)
+            L.ptab_p = (h, l, L.ptab)
+        return L.ptab_p
+
+    def _attention_tc(self, L, qkv, qkvp, outp, T, lens, B):
+        """qkv fp32 [M,3d] (queries), qkvp its fp16 pair (keys/values) -> outp pair [M,d]."""
+        d = self.d
+        ph, pl, _ = self._ptab_pair(L)
+        self._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, T, qkvp[0].data_ptr() + 2 * d, qkvp[1].data_ptr() + 2 * d,
+                qkvp[0].data_ptr() + 4 * d, qkvp[1].data_ptr() + 4 * d, 3 * d, T, _p(ph), _p(pl), d, _p(L.pos_u), _p(L.pos_v), None,
+                _p(outp[0]), _p(outp[1]), d, T, _p(lens), _p(lens), B, self.h, self.dk, T)
+
     def _tc(self, A, lda, W, bias, M, N, K, epi=EPI_BIAS, alpha=1.0, residual=None, ldr=0, C=None, Cp=None, ldc=0,
             tag="gemm"):
         """C / (Ch,Cl) = epi(A.W^T): A, W fp16 (h,l) pairs."""
@@ -216,6 +231,7 @@ class ConformerEngine:
             ws["t0p"] = (torch.empty(Mx, d, device=dev, dtype=f16), torch.empty(Mx, d, device=dev, dtype=f16))
             ws["t1p"] = (torch.empty(Mx, d, device=dev, dtype=f16), torch.empty(Mx, d, device=dev, dtype=f16))
             ws["hidp"] = (torch.empty(Mx, self.w.ffn, device=dev, dtype=f16), torch.empty(Mx, self.w.ffn, device=dev, dtype=f16))
+            ws["qkvp"] = (torch.empty(Mx, 3 * d, device=dev, dtype=f16), torch.empty(Mx, 3 * d, device=dev, dtype=f16))
         if len(self._ws) > 8:
             self._ws.clear()
         self._ws[key] = ws
@@ -350,10 +366,8 @@ class ConformerEngine:
             self._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
             self._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
             self._ln_split(x, L.ln_mha, t0p, M)
-            self._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, ldc=3 * d, tag="qkv_proj")
-            self._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, T, qkv.data_ptr() + 4 * d,
-                    qkv.data_ptr() + 8 * d, 3 * d, T, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]),
-                    d, T, _p(tlens), _p(tlens), B, self.h, self.dk, T)
+            self._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, Cp=ws["qkvp"], ldc=3 * d, tag="qkv_proj")
+            self._attention_tc(L, qkv, ws["qkvp"], t1p, T, tlens, B)
             self._tc(t1p, d, tw[i, "wo"], L.bo, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="out_proj")
             self._ln_split(x, L.ln_conv, t0p, M)
             self._tc(t0p, d, tw[i, "pw1"], L.pw1_b, M, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d, tag="pw1_glu")
@@ -486,7 +500,8 @@ class ConformerEngine:
         torch.cuda.synchronize(dev)
         n0 = self.launches
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # thread_local: other threads (e.g. the NCCL watchdog of torch.distributed) may keep issuing CUDA calls
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             g["ws"], g["status"], g["T"] = body()
         g["launches"] = self.launches - n0
         self.launches = n0
@@ -818,10 +833,8 @@ class EfficientConformerEngine(ConformerEngine):
                 self._k("attention", "masr_grouped_attention_f32", _p(qb), _p(kb), _p(vb), _p(L.ptab), d, Ti, _p(L.pos_u),
                         _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), _p(cur_lens), B, self.h, self.dk, self.GROUP, Ti)
             else:
-                self._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, ldc=3 * d, tag="qkv_proj")
-                self._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, Ti, qkv.data_ptr() + 4 * d,
-                        qkv.data_ptr() + 8 * d, 3 * d, Ti, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]),
-                        _p(t1p[1]), d, Ti, _p(cur_lens), _p(cur_lens), B, self.h, self.dk, Ti)
+                self._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, Cp=ws["qkvp"], ldc=3 * d, tag="qkv_proj")
+                self._attention_tc(L, qkv, ws["qkvp"], t1p, Ti, cur_lens, B)
             self._tc(t1p, d, tw[i, "wo"], L.bo, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="out_proj")
             self._ln_split(x, L.ln_conv, t0p, Mi)
             self._tc(t0p, d, tw[i, "pw1"], L.pw1_b, Mi, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d, tag="pw1_glu")

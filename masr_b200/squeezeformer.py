@@ -232,10 +232,8 @@ class SqueezeformerEngine(ConformerEngine):
                         _p(t0p[1]), cur_M, d)
             Mi, Ti = cur_M, cur_T
             # MHA (input pair = ada(x) in t0p) -> y = x + out_proj(att) -> x = LN1(y), pair(ada_ffn1(x))
-            self._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, ldc=3 * d, tag="qkv_proj")
-            self._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, Ti, qkv.data_ptr() + 4 * d, qkv.data_ptr() + 8 * d,
-                    3 * d, Ti, _p(L.ptab), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), d, Ti, _p(cur_lens),
-                    _p(cur_lens), B, self.h, self.dk, Ti)
+            self._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, Cp=ws["qkvp"], ldc=3 * d, tag="qkv_proj")
+            self._attention_tc(L, qkv, ws["qkvp"], t1p, Ti, cur_lens, B)
             self._tc(t1p, d, tw[i, "wo"], L.bo, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=y, ldc=d, tag="out_proj")
             self._ln_ada(y, L.ln1, x, L.ffn1_ada, t0p, Mi)
             # FFN1

@@ -1,0 +1,218 @@
+"""Many live streams on one GPU: batched chunk decoding for the streaming Conformer.
+
+The reference's streaming API is one stream per ``MASRPredictor`` (predict.py:237-343; ``forward_chunk`` asserts
+batch 1, conformer/encoder.py:378) and `infer_server.py` effectively serves one stream at a time.  BASELINE.json
+config 3/5 ask for dozens to hundreds of concurrent streams.  ``ConformerStreamPool`` keeps N slots of streaming state
+(attention K|V caches as fp16 pairs, conv left contexts, offsets) in one set of device buffers and advances every slot
+that has a chunk ready in ONE pass of tensor-core GEMMs (M = slots x 16 rows) — each slot computed exactly like the
+single-stream ``encode_chunk`` / reference ``forward_chunk`` with ``required_cache_size < 0`` (all history kept, which
+is what ``predict_stream`` passes).  ``StreamPool`` adds the per-stream host logic of ``predict_stream`` (sample
+carry-over with in-place dB renormalisation, 67/64/3 feature windowing, greedy history).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import EPI_BIAS_GLU, EPI_BIAS_SCALE, EPI_BIAS_SILU, EPI_RESIDUAL
+from .audio import pcm_bytes_to_float32, samples_to_float32
+from .engine import ConformerEngine, _p, greedy_score, subsampled_len
+from .predict import CACHED_FEATURE_NUM, DECODING_WINDOW, FRAME_SHIFT, chunk_starts
+from .text import ids_to_text
+
+CHUNK_FRAMES = DECODING_WINDOW          # 67 feature frames -> 16 encoder frames
+CHUNK_OUT = 16
+
+
+class ConformerStreamPool:
+    """Device state + one batched chunk step for `n_slots` streams."""
+
+    def __init__(self, eng: ConformerEngine, n_slots: int, max_frames: int = 3000):
+        if not eng.causal:
+            raise Exception("chunk decoding needs a streaming (causal) model")
+        if eng.gemm_path != "tc":
+            raise Exception("the stream pool runs on the tensor-core path")
+        self.eng, self.S, self.cap = eng, n_slots, max_frames
+        dev, d, w = eng.device, eng.d, eng.w
+        f16, f32 = torch.float16, torch.float32
+        nl = len(w.layers)
+        S, C = n_slots, CHUNK_OUT
+        self.lorder = w.kernel - 1
+        F1 = (CHUNK_FRAMES - 1) // 2
+        TH = (F1 + 1) // 2
+        M = S * C
+        self.kv = [(torch.zeros(S * self.cap, 2 * d, device=dev, dtype=f16), torch.zeros(S * self.cap, 2 * d, device=dev, dtype=f16))
+                   for _ in range(nl)]
+        self.xcat = torch.zeros(nl, S, self.lorder + C, d, device=dev, dtype=f32)
+        self.lens = torch.zeros(S, device=dev, dtype=torch.int32)           # cached frames per slot (== offset)
+        self.lens_host = [0] * S
+        self.b = {
+            "c1p": (torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16), torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16)),
+            "c2p": (torch.empty(M * eng.f2, d, device=dev, dtype=f16), torch.empty(M * eng.f2, d, device=dev, dtype=f16)),
+            "x": torch.empty(M, d, device=dev, dtype=f32), "t0": torch.empty(M, d, device=dev, dtype=f32),
+            "t0p": (torch.empty(M, d, device=dev, dtype=f16), torch.empty(M, d, device=dev, dtype=f16)),
+            "t1p": (torch.empty(M, d, device=dev, dtype=f16), torch.empty(M, d, device=dev, dtype=f16)),
+            "hidp": (torch.empty(M, w.ffn, device=dev, dtype=f16), torch.empty(M, w.ffn, device=dev, dtype=f16)),
+            "qkv": torch.empty(M, 3 * d, device=dev, dtype=f32),
+            "qkvp": (torch.empty(M, 3 * d, device=dev, dtype=f16), torch.empty(M, 3 * d, device=dev, dtype=f16)),
+            "xcp": (torch.empty(S * (self.lorder + C), d, device=dev, dtype=f16), torch.empty(S * (self.lorder + C), d, device=dev, dtype=f16)),
+            "g": torch.empty(S * (self.lorder + C), d, device=dev, dtype=f32),
+            "logits": torch.empty(M, eng.Vpad, device=dev, dtype=f32),
+            "ids": torch.empty(M, device=dev, dtype=torch.int32), "maxp": torch.empty(M, device=dev, dtype=f32),
+            "qlen": torch.zeros(S, device=dev, dtype=torch.int32), "klen": torch.zeros(S, device=dev, dtype=torch.int32),
+            "clen": torch.full((S,), self.lorder + C, device=dev, dtype=torch.int32),
+        }
+
+    def reset(self, slot: int):
+        """``InferencePredictor.reset_stream`` for one slot (inference_predictor.py:97-102)."""
+        self.lens_host[slot] = 0
+        self.lens[slot] = 0
+        self.xcat[:, slot].zero_()
+
+    def step(self, feats: torch.Tensor, nframes: Sequence[int]):
+        """feats [S, 67, 80] raw log-mel (device), nframes[s] = valid feature frames of slot s this round (0 = idle).
+        -> (ids [S,16] int32, maxp [S,16]) device tensors; the first ((n-1)//2-1)//2 entries of each row are valid."""
+        eng, S, C, cap = self.eng, self.S, CHUNK_OUT, self.cap
+        w, d, tw, b = eng.w, eng.d, eng._tcw, self.b
+        dev = eng.device
+        tout = [subsampled_len(int(n)) for n in nframes]
+        for s in range(S):
+            if self.lens_host[s] + tout[s] > cap or self.lens_host[s] + tout[s] >= w.max_len:
+                raise AssertionError(f"stream slot {s}: {self.lens_host[s] + tout[s]} cached frames exceed the pool capacity")
+        qlen = torch.tensor(tout, dtype=torch.int32)
+        klen = torch.tensor([self.lens_host[s] + tout[s] for s in range(S)], dtype=torch.int32)
+        b["qlen"].copy_(qlen)
+        b["klen"].copy_(klen)
+        # destination rows of the new K|V rows in the per-slot caches
+        rows = torch.tensor([s * cap + self.lens_host[s] + t for s in range(S) for t in range(tout[s])], dtype=torch.int64, device=dev)
+        src = torch.tensor([s * C + t for s in range(S) for t in range(tout[s])], dtype=torch.int64, device=dev)
+        M = S * C
+        F1 = (CHUNK_FRAMES - 1) // 2
+        x, t0, t0p, t1p, hidp, qkv, qkvp, g, xcp = b["x"], b["t0"], b["t0p"], b["t1p"], b["hidp"], b["qkv"], b["qkvp"], b["g"], b["xcp"]
+        eng._k("conv1", "masr_conv1_cmvn_relu_planes_f16", _p(feats), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w), _p(w.conv1_b),
+               _p(b["c1p"][0]), _p(b["c1p"][1]), S, CHUNK_FRAMES, w.idim, F1, eng.w1_cols, d)
+        eng._k("conv2", "masr_conv2_tc_f16x2", _p(b["c1p"][0]), _p(b["c1p"][1]), _p(tw["conv2"][0]), _p(tw["conv2"][1]), _p(w.conv2_b),
+               None, _p(b["c2p"][0]), _p(b["c2p"][1]), S, F1, C, d)
+        eng._tc(b["c2p"], eng.f2 * d, tw["embed"], w.embed_b, M, d, eng.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5, C=x, ldc=d)
+        LC = self.lorder + C
+        for i, L in enumerate(w.layers):
+            eng._ln_split(x, L.ln_ffm, t0p, M)
+            eng._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
+            eng._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d)
+            eng._ln_split(x, L.ln_mha, t0p, M)
+            eng._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, Cp=qkvp, ldc=3 * d)
+            kvh, kvl = self.kv[i]
+            if rows.numel():
+                kvh.index_copy_(0, rows, qkvp[0].index_select(0, src)[:, d:])
+                kvl.index_copy_(0, rows, qkvp[1].index_select(0, src)[:, d:])
+            ph, pl, _ = eng._ptab_pair(L)
+            eng._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, C, kvh.data_ptr(), kvl.data_ptr(), kvh.data_ptr() + 2 * d,
+                   kvl.data_ptr() + 2 * d, 2 * d, cap, _p(ph), _p(pl), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), d, C,
+                   _p(b["qlen"]), _p(b["klen"]), S, eng.h, eng.dk, C)
+            eng._tc(t1p, d, tw[i, "wo"], L.bo, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d)
+            # conv module over [cache ++ chunk] per slot (convolution.py:101-109)
+            eng._ln(x, L.ln_conv, t0, M)
+            xc = self.xcat[i]                                   # [S, 14+16, d]
+            xc[:, self.lorder:].copy_(t0.view(S, C, d))
+            eng._k("affine_split", "masr_affine_split_f16", _p(xc), None, None, _p(xcp[0]), _p(xcp[1]), S * LC, d)
+            eng._tc(xcp, d, tw[i, "pw1"], L.pw1_b, S * LC, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d)
+            eng._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, LC, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]), None, None,
+                   _p(t1p[0]), _p(t1p[1]), d, C, _p(b["clen"]), S, d, w.kernel, 0, C, 1e-5)
+            # new left context = the last `lorder` VALID rows: rows [tout, tout+lorder) of [cache ++ chunk]
+            if all(t == C for t in tout):
+                xc[:, :self.lorder].copy_(xc[:, C:C + self.lorder].clone())
+            else:
+                for s in range(S):
+                    if tout[s]:
+                        xc[s, :self.lorder].copy_(xc[s, tout[s]:tout[s] + self.lorder].clone())
+            eng._tc(t1p, d, tw[i, "pw2"], L.pw2_b, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d)
+            eng._ln_split(x, L.ln_ff, t0p, M)
+            eng._tc(t0p, d, tw[i, "ff1"], L.ff[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
+            eng._tc(hidp, w.ffn, tw[i, "ff2"], L.ff[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d)
+            eng._ln(x, L.ln_final, x, M)
+        eng._ln_split(x, w.after_norm, t0p, M)
+        eng._tc(t0p, d, tw["ctc"], w.ctc_b, M, eng.V, d, C=b["logits"], ldc=eng.Vpad)
+        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
+        for s in range(S):
+            self.lens_host[s] += tout[s]
+        return b["ids"].view(S, C), b["maxp"].view(S, C), tout
+
+
+class StreamPool:
+    """`predict_stream` for many streams at once (same per-stream results as one ``MASRPredictor`` per stream)."""
+
+    def __init__(self, eng: ConformerEngine, vocab: Sequence[str], n_slots: int, use_db_normalization: bool = True,
+                 target_db: float = -20.0, max_frames: int = 3000):
+        self.eng, self.vocab, self.S = eng, list(vocab), n_slots
+        self.pool = ConformerStreamPool(eng, n_slots, max_frames)
+        self.use_db, self.target_db = use_db_normalization, target_db
+        self.remained: List[Optional[np.ndarray]] = [None] * n_slots
+        self.cached: List[Optional[torch.Tensor]] = [None] * n_slots
+        self.hist_ids: List[List[int]] = [[] for _ in range(n_slots)]
+        self.hist_p: List[list] = [[] for _ in range(n_slots)]
+
+    def reset_stream(self, slot: int):
+        self.pool.reset(slot)
+        self.remained[slot], self.cached[slot] = None, None
+        self.hist_ids[slot], self.hist_p[slot] = [], []
+
+    def push(self, audio: Dict[int, object], is_end: bool = False, channels: int = 1, samp_width: int = 2):
+        """audio: slot -> np.ndarray | PCM bytes (one push per slot).  -> slot -> {'text','score'} | None, exactly what
+        ``MASRPredictor.predict_stream(chunk, is_end)`` would return for that stream."""
+        eng, S = self.eng, self.S
+        slots = sorted(audio)
+        for s in slots:
+            a = audio[s]
+            new = samples_to_float32(a) if isinstance(a, np.ndarray) else pcm_bytes_to_float32(a, channels, samp_width)
+            self.remained[s] = new if self.remained[s] is None else np.concatenate([self.remained[s], new])
+        # one batched fbank over every slot's un-consumed samples; the tail keeps the gain (predict.py:274)
+        feats, frames, status = eng.fbank([self.remained[s] for s in slots], self.use_db, self.target_db)
+        gains = eng.last_gain.cpu().numpy() if self.use_db else np.ones(len(slots), np.float32)
+        if np.any(status.cpu().numpy() != 0):
+            raise ValueError("无法将段规范化到目标dB，音频增益已经超过max_gain_db (300.0dB)")
+        for j, s in enumerate(slots):
+            nf = frames[j]
+            xc = feats[j, :nf]
+            self.cached[s] = xc if self.cached[s] is None else torch.cat([self.cached[s], xc], dim=0)
+            tail = self.remained[s][FRAME_SHIFT * nf:]
+            self.remained[s] = (tail * np.float32(gains[j])).astype(np.float32) if self.use_db else tail
+        pending = {s: chunk_starts(int(self.cached[s].shape[0]), is_end) for s in slots}
+        touched = {s: bool(pending[s]) for s in slots}
+        ends = {}
+        rounds = max((len(v) for v in pending.values()), default=0)
+        batch = torch.zeros(S, CHUNK_FRAMES, 80, device=eng.device, dtype=torch.float32)
+        for r in range(rounds):
+            nfr = [0] * S
+            for s in slots:
+                if r < len(pending[s]):
+                    cur = pending[s][r]
+                    end = min(cur + CHUNK_FRAMES, int(self.cached[s].shape[0]))
+                    batch[s, :end - cur].copy_(self.cached[s][cur:end])
+                    nfr[s] = end - cur
+                    ends[s] = end
+            ids, maxp, tout = self.pool.step(batch, nfr)
+            ids_h, mp_h = ids.cpu().numpy(), maxp.cpu().numpy()
+            for s in slots:
+                for t in range(tout[s]):
+                    i = int(ids_h[s, t])
+                    self.hist_ids[s].append(i)
+                    if i != 0:
+                        self.hist_p[s].append(mp_h[s, t])
+        out = {}
+        for s in slots:
+            if not touched[s]:
+                out[s] = None
+                continue
+            self.cached[s] = self.cached[s][ends[s] - CACHED_FEATURE_NUM:]
+            toks, prev = [], None
+            for i in self.hist_ids[s]:
+                if i != prev and i != 0:
+                    toks.append(i)
+                prev = i
+            acc = np.float32(0.0)
+            for p in self.hist_p[s]:
+                acc = np.float32(acc + p)
+            out[s] = {"text": ids_to_text(toks, self.vocab), "score": greedy_score(acc, len(self.hist_p[s]))}
+        return out

@@ -111,8 +111,19 @@ def test_relpos_attention(rt, lens, fn):
     qd, pd, ud, vd = qkv.to(rt.dev), Ptab.to(rt.dev), u.to(rt.dev), v.to(rt.dev)
     ld = torch.tensor(lens, dtype=torch.int32, device=rt.dev)
     out = torch.full((B, T, d), float("nan"), device=rt.dev)
-    rt.call(fn, P(qd), 3 * d, T, qd.data_ptr() + 4 * d, qd.data_ptr() + 8 * d, 3 * d, T,
-            P(pd), d, P(ud), P(vd), P(out), None, None, d, T, P(ld), P(ld), B, H, dk, T, rt.st())
+    if fn == "masr_relpos_attention_tc":
+        def split(x):
+            x = x.contiguous()
+            h = torch.empty(x.shape, dtype=torch.float16, device=rt.dev); l = torch.empty_like(h)
+            rt.call("masr_split_f16", P(x), P(h), P(l), x.numel(), rt.st())
+            return h, l
+        qh, ql = split(qd)
+        ph, pl = split(pd)
+        rt.call(fn, P(qd), 3 * d, T, qh.data_ptr() + 2 * d, ql.data_ptr() + 2 * d, qh.data_ptr() + 4 * d, ql.data_ptr() + 4 * d,
+                3 * d, T, P(ph), P(pl), d, P(ud), P(vd), P(out), None, None, d, T, P(ld), P(ld), B, H, dk, T, rt.st())
+    else:
+        rt.call(fn, P(qd), 3 * d, T, qd.data_ptr() + 4 * d, qd.data_ptr() + 8 * d, 3 * d, T,
+                P(pd), d, P(ud), P(vd), P(out), None, None, d, T, P(ld), P(ld), B, H, dk, T, rt.st())
     out = out.cpu()
     for b, n in enumerate(lens):
         q = qkv[b, :n, :d].view(n, H, dk); k = qkv[b, :n, d:2 * d].view(n, H, dk).transpose(0, 1)
