@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -32,6 +33,7 @@ constexpr int TSTAGES = 3;
 constexpr int TILE_BYTES = TBM * TBK * 2;              // 16 KB: one operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;            // Ah, Al, Wh, Wl
 constexpr int EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 4096;                  // per epilogue warp: one 32 x 32 fp32 block
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 constexpr uint32_t TMEM_COLS = 512;                    // 2 x main (ping-pong) + correction accumulator, 128 fp32 columns each (384 -> 512)
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
@@ -117,7 +119,17 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, __half2& h, __ha
 // Epilogue activations on the SFU (ex2.approx / rcp.approx, <= 2 ulp each): the accurate expf + IEEE divide
 // cost ~40 instructions per element and made the FFN w_1 epilogue 2.6x longer than its MMA main loop.
 // Absolute error < 2e-7 on silu/sigmoid outputs, inside the fp32-grade budget (tests/test_gpu_tc_gemm.py).
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
 __device__ __forceinline__ float fast_silu(float x) { return x * fast_sigmoid(x); }
 
 struct TcParams {
@@ -132,6 +144,7 @@ struct TcParams {
     float alpha;
     // conv mode (implicit GEMM over parity planes of the conv-1 activation)
     int conv_T2;       // output rows per utterance (T2max)
+    int flags;         // bit 0: stage epilogue stores through shared memory (row-contiguous global writes)
 };
 
 struct TcMaps {
@@ -151,38 +164,149 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-// One 32-column slice of a finished output row: bias was already added; apply the epilogue and store
-// (fp32 and/or the fp16 (h,l) pair).  `n` is the global column of v[0]; warp-uniform except row_ok.
-__device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[32], int n, int64_t out_row, bool row_ok) {
-    if (n >= p.N || !row_ok) return;
-    const bool vec_c = (p.ldc & 3) == 0;
-    if (p.epi == MASR_EPI_BIAS_GLU) {
-        // interleaved (value, gate) columns -> 16 outputs at column n/2
-        float o[16];
+// ---- epilogue stores ------------------------------------------------------------------------------
+// A TMEM lane is an output row, so each epilogue thread holds 32 consecutive columns of ONE row: storing
+// straight from registers makes every warp store touch 32 different 128-byte lines, 16 bytes each (ncu:
+// the store pipe, not the tensor pipe, bounded the K=256 GEMMs).  Each warp therefore transposes its
+// 32 x 32 block through a private, XOR-swizzled 4 KB shared-memory buffer (conflict-free both ways) and
+// writes it back row-contiguous: every store instruction covers whole lines (4 rows x 128 B for fp32).
+struct EpiCtx {
+    uint8_t* sb;        // this warp's 4 KB staging buffer
+    int lane;
+    int64_t row0;       // global output row of lane 0
+    int nvalid;         // rows of this warp's 32 that exist
+};
+
+// regs: CH 16-byte pieces = this thread's row segment.  g0: address of (row0, first column of the segment).
+template <int CH>
+__device__ __forceinline__ void staged_store(const EpiCtx& c, const uint4 (&regs)[CH], uint8_t* g0, int64_t pitch_bytes) {
+    constexpr int RSH = (CH == 8) ? 0 : (CH == 4) ? 1 : 2;
+    constexpr int RPI = 32 / CH;                                  // rows per store instruction
+    __syncwarp();                                                 // the previous block has been read back
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * fast_sigmoid(v[2 * j + 1]);
-        const int nn = n >> 1;
-        if (p.C) {
-            float* cp = p.C + out_row * p.ldc + nn;
+    for (int k = 0; k < CH; ++k)
+        *reinterpret_cast<uint4*>(c.sb + c.lane * (CH * 16) + ((k ^ ((c.lane >> RSH) & (CH - 1))) << 4)) = regs[k];
+    __syncwarp();
+    const int sub = c.lane / CH, k = c.lane % CH;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    for (int i = 0; i < CH; ++i) {
+        const int row = i * RPI + sub;
+        const uint4 v = *reinterpret_cast<const uint4*>(c.sb + row * (CH * 16) + ((k ^ ((row >> RSH) & (CH - 1))) << 4));
+        if (row < c.nvalid) *reinterpret_cast<uint4*>(g0 + row * pitch_bytes + (k << 4)) = v;
+    }
+}
+
+// inverse of staged_store for CH = 8: fetch a 32-row x 128-byte block row-contiguous, hand each thread its row
+__device__ __forceinline__ void staged_load(const EpiCtx& c, uint4 (&regs)[8], const uint8_t* g0, int64_t pitch_bytes) {
+    __syncwarp();
+    const int sub = c.lane >> 3, k = c.lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + sub;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < c.nvalid) v = *reinterpret_cast<const uint4*>(g0 + row * pitch_bytes + (k << 4));
+        *reinterpret_cast<uint4*>(c.sb + row * 128 + ((k ^ (row & 7)) << 4)) = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2)
+        regs[k2] = *reinterpret_cast<const uint4*>(c.sb + c.lane * 128 + ((k2 ^ (c.lane & 7)) << 4));
+}
+
+// W fp32 outputs of this thread's row (W = 32, or 16 after GLU) at output column n -> fp32 C and/or (h,l) pair
+template <int W>
+__device__ __forceinline__ void emit(const TcParams& p, const EpiCtx& c, const float (&o)[W], int n, int n_limit) {
+    const bool full = n + W - 1 < n_limit;
+    const bool row_ok = c.lane < c.nvalid;
+    const int64_t my_row = c.row0 + c.lane;
+    if (p.C) {
+        if ((p.flags & 1) && full && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
+            uint4 regs[W / 4];
+#pragma unroll
+            for (int j = 0; j < W / 4; ++j)
+                regs[j] = make_uint4(__float_as_uint(o[4 * j]), __float_as_uint(o[4 * j + 1]), __float_as_uint(o[4 * j + 2]),
+                                     __float_as_uint(o[4 * j + 3]));
+            staged_store<W / 4>(c, regs, reinterpret_cast<uint8_t*>(p.C + c.row0 * p.ldc + n), p.ldc * 4);
+        } else if (row_ok && full && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
+            float* cp = p.C + my_row * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < W; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else if (row_ok) {
+            float* cp = p.C + my_row * p.ldc + n;
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (n + j < n_limit) cp[j] = o[j];
         }
-        if (p.Ch) {
-            __align__(16) __half2 hh[8], ll[8];
+    }
+    if (p.Ch) {
+        uint32_t hh[W / 2], ll[W / 2];                       // packed half2 bit patterns (kept in registers)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) split_f16x2(o[2 * j], o[2 * j + 1], hh[j], ll[j]);
+        for (int j = 0; j < W / 2; ++j) {
+            __half2 h2, l2;
+            split_f16x2(o[2 * j], o[2 * j + 1], h2, l2);
+            hh[j] = *reinterpret_cast<uint32_t*>(&h2);
+            ll[j] = *reinterpret_cast<uint32_t*>(&l2);
+        }
+        if ((p.flags & 1) && full && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.Ch) | reinterpret_cast<uintptr_t>(p.Cl)) & 15) == 0) {
+            uint4 regs[W / 8];
 #pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-                *reinterpret_cast<uint4*>(p.Ch + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&hh[j / 2]);
-                *reinterpret_cast<uint4*>(p.Cl + out_row * p.ldc + nn + j) = *reinterpret_cast<const uint4*>(&ll[j / 2]);
+            for (int j = 0; j < W / 8; ++j) regs[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+            staged_store<W / 8>(c, regs, reinterpret_cast<uint8_t*>(p.Ch + c.row0 * p.ldc + n), p.ldc * 2);
+#pragma unroll
+            for (int j = 0; j < W / 8; ++j) regs[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
+            staged_store<W / 8>(c, regs, reinterpret_cast<uint8_t*>(p.Cl + c.row0 * p.ldc + n), p.ldc * 2);
+        } else if (row_ok && full && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.Ch) | reinterpret_cast<uintptr_t>(p.Cl)) & 15) == 0) {
+            uint4* hp = reinterpret_cast<uint4*>(p.Ch + my_row * p.ldc + n);
+            uint4* lp = reinterpret_cast<uint4*>(p.Cl + my_row * p.ldc + n);
+#pragma unroll
+            for (int j = 0; j < W / 8; ++j) {
+                hp[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+                lp[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
+            }
+        } else if (row_ok) {
+            unsigned short* hp = reinterpret_cast<unsigned short*>(p.Ch + my_row * p.ldc + n);
+            unsigned short* lp = reinterpret_cast<unsigned short*>(p.Cl + my_row * p.ldc + n);
+#pragma unroll
+            for (int j = 0; j < W / 2; ++j) {
+                if (n + 2 * j < n_limit) { hp[2 * j] = (unsigned short)(hh[j] & 0xffff); lp[2 * j] = (unsigned short)(ll[j] & 0xffff); }
+                if (n + 2 * j + 1 < n_limit) { hp[2 * j + 1] = (unsigned short)(hh[j] >> 16); lp[2 * j + 1] = (unsigned short)(ll[j] >> 16); }
             }
         }
+    }
+}
+
+// One 32-column slice of a finished output row: bias was already added; apply the epilogue and store.
+// `n` is the global column of v[0] (warp-uniform).
+__device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, float (&v)[32], int n) {
+    if (p.epi == MASR_EPI_BIAS_GLU) {
+        // interleaved (value, gate) columns -> 16 outputs at column n/2 of an N/2-wide output
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+            float e[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) e[k] = ex2_approx(v[2 * (j + k) + 1] * -1.4426950408889634f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) e[k] = rcp_approx(1.0f + e[k]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[j + k] = v[2 * (j + k)] * e[k];
+        }
+        emit<16>(p, c, o, n >> 1, p.N >> 1);
         return;
     }
     switch (p.epi) {
         case MASR_EPI_BIAS_SILU:
+            // eight independent SFU chains at a time (a one-register serial chain was 5x slower than the MMA loop)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
+            for (int j = 0; j < 32; j += 8) {
+                float e[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = ex2_approx(v[j + k] * -1.4426950408889634f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = rcp_approx(1.0f + e[k]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[j + k] *= e[k];
+            }
             break;
         case MASR_EPI_BIAS_RELU:
 #pragma unroll
@@ -193,16 +317,27 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[32], i
             for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
             break;
         case MASR_EPI_RESIDUAL: {
-            const float* r = p.residual + out_row * p.ldr + n;
             const bool vec_r = (p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
-            if (n + 31 < p.N && vec_r) {
+            if ((p.flags & 2) && n + 31 < p.N && vec_r) {
+                uint4 rr[8];
+                staged_load(c, rr, reinterpret_cast<const uint8_t*>(p.residual + c.row0 * p.ldr + n), p.ldr * 4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[4 * j] = __uint_as_float(rr[j].x) + p.alpha * v[4 * j];
+                    v[4 * j + 1] = __uint_as_float(rr[j].y) + p.alpha * v[4 * j + 1];
+                    v[4 * j + 2] = __uint_as_float(rr[j].z) + p.alpha * v[4 * j + 2];
+                    v[4 * j + 3] = __uint_as_float(rr[j].w) + p.alpha * v[4 * j + 3];
+                }
+            } else if (c.lane < c.nvalid && n + 31 < p.N && vec_r) {
+                const float* r = p.residual + (c.row0 + c.lane) * p.ldr + n;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    float4 rv = *reinterpret_cast<const float4*>(r + j);
+                    const float4 rv = *reinterpret_cast<const float4*>(r + j);
                     v[j] = rv.x + p.alpha * v[j]; v[j + 1] = rv.y + p.alpha * v[j + 1];
                     v[j + 2] = rv.z + p.alpha * v[j + 2]; v[j + 3] = rv.w + p.alpha * v[j + 3];
                 }
-            } else {
+            } else if (c.lane < c.nvalid) {
+                const float* r = p.residual + (c.row0 + c.lane) * p.ldr + n;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (n + j < p.N) v[j] = r[j] + p.alpha * v[j];
@@ -211,38 +346,7 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, float (&v)[32], i
         }
         default: break;
     }
-    const bool full = n + 31 < p.N;
-    if (p.C) {
-        float* cp = p.C + out_row * p.ldc + n;
-        if (full && vec_c) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n + j < p.N) cp[j] = v[j];
-        }
-    }
-    if (p.Ch) {
-        __align__(16) __half2 hh[16], ll[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hh[j], ll[j]);
-        __half* hp = p.Ch + out_row * p.ldc + n;
-        __half* lp = p.Cl + out_row * p.ldc + n;
-        if (full && (p.ldc & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                *reinterpret_cast<uint4*>(hp + j) = *reinterpret_cast<const uint4*>(&hh[j / 2]);
-                *reinterpret_cast<uint4*>(lp + j) = *reinterpret_cast<const uint4*>(&ll[j / 2]);
-            }
-        } else {
-            const __half* hs = reinterpret_cast<const __half*>(hh);
-            const __half* ls = reinterpret_cast<const __half*>(ll);
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n + j < p.N) { hp[j] = hs[j]; lp[j] = ls[j]; }
-        }
-    }
+    emit<32>(p, c, v, n, p.N);
 }
 
 // Accumulation: the tensor core adds into its fp32 TMEM accumulator with truncation, so a long K loop
@@ -259,7 +363,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, int tiles_n, int tiles_t) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TSTAGES * STAGE_BYTES);
+    uint8_t* epi_stage = smem + TSTAGES * STAGE_BYTES;                // EPI_WARPS x 4 KB (see staged_store)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + TSTAGES;
     uint64_t* main_full = empty_bar + TSTAGES;     // [2]
     uint64_t* main_empty = main_full + 2;          // [2]
@@ -363,13 +468,62 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     } else {
         // ---- 8 epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----
         const int q = warp & 3, half = (warp - 2) >> 2;
-        const int r_tile = q * 32 + lane;                              // row of the 128-row tile
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * (TBN / 2);
         const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+        EpiCtx ctx;
+        ctx.sb = epi_stage + (warp - 2) * EPI_STAGE_BYTES;
+        ctx.lane = lane;
         uint32_t cg = 0, tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             int n0, m0, t0, b;
             decode(tile, n0, m0, t0, b);
+            const int nw = n0 + half * (TBN / 2);                      // first column of this warp
+            // bias of the warp's 64 columns: lane l keeps columns l and 32+l, broadcast by shuffle below;
+            // fetched before the accumulator wait so its latency is hidden
+            float bias0 = 0.f, bias1 = 0.f;
+            if (p.bias != nullptr) {
+                if (nw + lane < p.N) bias0 = __ldg(p.bias + nw + lane);
+                if (nw + 32 + lane < p.N) bias1 = __ldg(p.bias + nw + 32 + lane);
+            }
+            // row mapping: the warp's 32 tile rows are 32 consecutive output rows in both modes
+            if (CONV) {
+                // tile row r = ti*19 + f  ->  output row (b*T2 + t0)*19 + r, for r < 114 and t0 + ti < T2
+                const int rows = min(CONV_ROWS, (p.conv_T2 - t0) * CONV_W2);
+                ctx.row0 = ((int64_t)b * p.conv_T2 + t0) * CONV_W2 + q * 32;
+                ctx.nvalid = max(0, min(32, rows - q * 32));
+            } else {
+                ctx.row0 = (int64_t)m0 + q * 32;
+                ctx.nvalid = max(0, min(32, p.M - (m0 + q * 32)));
+            }
+            if (nchunks == 1) {
+                // K <= 256: main and correction accumulators complete together; go straight from TMEM to the
+                // stores 32 columns at a time (no 64-register running sum, so the activations keep their ILP)
+                mbar_wait(&main_full[cg & 1], (cg >> 1) & 1);
+                mbar_wait(&corr_full[tl & 1], (tl >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < TBN / 64; ++cc) {
+                    uint32_t r[32], rc[32];
+                    tmem_ld32(lane_base + (cg & 1) * TBN + cc * 32, r);
+                    tmem_ld32(lane_base + 2 * TBN + (tl & 1) * TBN + cc * 32, rc);
+                    tmem_ld_wait();
+                    if (cc == TBN / 64 - 1) {                          // TMEM released: the rest runs from registers
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive(&main_empty[cg & 1]); mbar_arrive(&corr_empty[tl & 1]); }
+                    }
+                    const int n = nw + cc * 32;
+                    if (n >= p.N) continue;                            // warp-uniform
+                    float v[32];
+                    const float bsrc = cc ? bias1 : bias0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        v[j] = fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])) + __shfl_sync(0xffffffffu, bsrc, j);
+                    store_chunk(p, ctx, v, n);
+                }
+                ++cg;
+                continue;
+            }
             float acc[TBN / 2];
 #pragma unroll
             for (int j = 0; j < TBN / 2; ++j) acc[j] = 0.f;
@@ -401,30 +555,16 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&corr_empty[tl & 1]);           // TMEM released: the rest runs from registers
-            // row mapping
-            int64_t out_row;
-            bool row_ok;
-            if (CONV) {
-                const int ti = r_tile / CONV_W2, f = r_tile - ti * CONV_W2;
-                const int t = t0 + ti;
-                row_ok = r_tile < CONV_ROWS && t < p.conv_T2;
-                out_row = ((int64_t)b * p.conv_T2 + t) * CONV_W2 + f;
-            } else {
-                out_row = m0 + r_tile;
-                row_ok = out_row < p.M;
-            }
 #pragma unroll
             for (int cc = 0; cc < TBN / 64; ++cc) {
-                const int n = n0 + half * (TBN / 2) + cc * 32;
+                const int n = nw + cc * 32;
+                if (n >= p.N) break;                                   // warp-uniform
                 float v[32];
+                const float bsrc = cc ? bias1 : bias0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float bb = (p.bias != nullptr && n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
-                    v[j] = acc[cc * 32 + j] + bb;
-                }
-                store_chunk(p, v, n, out_row, row_ok);
+                for (int j = 0; j < 32; ++j) v[j] = acc[cc * 32 + j] + __shfl_sync(0xffffffffu, bsrc, j);
+                store_chunk(p, ctx, v, n);
             }
-            __syncwarp();
         }
     }
     tc_fence_before();
@@ -436,7 +576,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     }
 }
 
-constexpr size_t kTcSmem = TSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + tmem slot*/;
+constexpr size_t kTcSmem = TSTAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + tmem slot*/;
+static_assert(kTcSmem <= 232448, "tc_gemm shared memory exceeds the 227 KB per-CTA limit of sm_100");
 
 // ---- fp32 -> (h,l) split, elementwise (weights at load time; activations produced by SIMT kernels) ----
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, __half* __restrict__ h,
@@ -503,6 +644,14 @@ static int make_map_plane(CUtensorMap* map, const void* ptr, int B, int TH, int 
     return MASR_OK;
 }
 
+// Epilogue flags.  Default 1 = staged (row-contiguous) stores: measured on B200 (tools/gemm_bench.py, M=7936)
+// ffn_w1 58.5 -> 42.1 us, qkv 35.5 -> 23.5 us, ctc head 91 -> 63 us; staging the residual READ as well (bit 1)
+// did not pay (w_2 31 -> 35 us).  MASR_TC_FLAGS overrides for A/B runs.
+static int tc_flags() {
+    const char* e = getenv("MASR_TC_FLAGS");
+    return e ? atoi(e) : 1;
+}
+
 static int num_sms() {
     static int n[64] = {0};
     int dev = 0;
@@ -554,7 +703,7 @@ extern "C" int masr_conv2_tc_f16x2(const void* c1h, const void* c1l, const void*
     if ((rc = make_map_2d(&maps.w[0], Wh, C, 9 * C, 9 * C))) return rc;
     if ((rc = make_map_2d(&maps.w[1], Wl, C, 9 * C, 9 * C))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
-    TcParams p{bias, nullptr, out, (__half*)outh, (__half*)outl, 0, C, B * T2 * CONV_W2, C, 9 * C, MASR_EPI_BIAS_RELU, 1.f, T2};
+    TcParams p{bias, nullptr, out, (__half*)outh, (__half*)outl, 0, C, B * T2 * CONV_W2, C, 9 * C, MASR_EPI_BIAS_RELU, 1.f, T2, tc_flags()};
     const int tiles_n = (C + TBN - 1) / TBN, tiles_t = (T2 + CONV_TR - 1) / CONV_TR;
     const int num_tiles = tiles_n * tiles_t * B;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
@@ -593,7 +742,7 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     if ((rc = make_map_2d(&maps.w[0], Wh, N, K, K))) return rc;
     if ((rc = make_map_2d(&maps.w[1], Wl, N, K, K))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
-    TcParams p{bias, residual, C, (__half*)Ch, (__half*)Cl, ldr, ldc, M, N, K, epilogue, alpha, 0};
+    TcParams p{bias, residual, C, (__half*)Ch, (__half*)Cl, ldr, ldc, M, N, K, epilogue, alpha, 0, tc_flags()};
     const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = tiles_n * tiles_m;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
