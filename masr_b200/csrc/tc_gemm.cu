@@ -32,9 +32,8 @@ constexpr int TBM = 128, TBN = 128, TBK = 64;
 constexpr int TSTAGES = 3;
 constexpr int TILE_BYTES = TBM * TBK * 2;              // 16 KB: one operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;            // Ah, Al, Wh, Wl
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_STAGE_BYTES = 4096;                  // per epilogue warp: one 32 x 32 fp32 block
-constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
+constexpr int EPI_STAGE_TOTAL = 32768;                 // epilogue store staging, split evenly over the epilogue warps
+constexpr int tc_threads(int ew) { return 64 + 32 * ew; }   // TMA warp + MMA warp + EW epilogue warps
 constexpr uint32_t TMEM_COLS = 512;                    // 2 x main (ping-pong) + correction accumulator, 128 fp32 columns each (384 -> 512)
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 
@@ -171,62 +170,87 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
 // 32 x 32 block through a private, XOR-swizzled 4 KB shared-memory buffer (conflict-free both ways) and
 // writes it back row-contiguous: every store instruction covers whole lines (4 rows x 128 B for fp32).
 struct EpiCtx {
-    uint8_t* sb;        // this warp's 4 KB staging buffer
+    uint32_t sb;        // shared-space address of this warp's staging buffer (4 KB with 8 epilogue warps, 2 KB with 16)
     int lane;
     int64_t row0;       // global output row of lane 0
     int nvalid;         // rows of this warp's 32 that exist
 };
 
-// regs: CH 16-byte pieces = this thread's row segment.  g0: address of (row0, first column of the segment).
+// explicit shared-space accesses: through a generic pointer these compiled to LD.E/ST.E (generic), whose
+// latency the 2-warps-per-scheduler epilogue could not hide (ncu: 25 % of its samples waited on them)
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
+// regs: CH 16-byte pieces = this thread's row segment (needs CH * 512 bytes of staging).
+// g0: address of (row0, first column of the segment).
 template <int CH>
 __device__ __forceinline__ void staged_store(const EpiCtx& c, const uint4 (&regs)[CH], uint8_t* g0, int64_t pitch_bytes) {
     constexpr int RSH = (CH == 8) ? 0 : (CH == 4) ? 1 : 2;
     constexpr int RPI = 32 / CH;                                  // rows per store instruction
     __syncwarp();                                                 // the previous block has been read back
 #pragma unroll
-    for (int k = 0; k < CH; ++k)
-        *reinterpret_cast<uint4*>(c.sb + c.lane * (CH * 16) + ((k ^ ((c.lane >> RSH) & (CH - 1))) << 4)) = regs[k];
+    for (int k = 0; k < CH; ++k) sts128(c.sb + c.lane * (CH * 16) + ((k ^ ((c.lane >> RSH) & (CH - 1))) << 4), regs[k]);
     __syncwarp();
     const int sub = c.lane / CH, k = c.lane % CH;
+    uint4 v[CH];
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
         const int row = i * RPI + sub;
-        const uint4 v = *reinterpret_cast<const uint4*>(c.sb + row * (CH * 16) + ((k ^ ((row >> RSH) & (CH - 1))) << 4));
-        if (row < c.nvalid) *reinterpret_cast<uint4*>(g0 + row * pitch_bytes + (k << 4)) = v;
+        v[i] = lds128(c.sb + row * (CH * 16) + ((k ^ ((row >> RSH) & (CH - 1))) << 4));
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const int row = i * RPI + sub;
+        if (row < c.nvalid) *reinterpret_cast<uint4*>(g0 + row * pitch_bytes + (k << 4)) = v[i];
     }
 }
 
-// inverse of staged_store for CH = 8: fetch a 32-row x 128-byte block row-contiguous, hand each thread its row
+// inverse of staged_store for CH = 8 (4 KB staging): fetch a 32-row x 128-byte block row-contiguous, hand each thread its row
 __device__ __forceinline__ void staged_load(const EpiCtx& c, uint4 (&regs)[8], const uint8_t* g0, int64_t pitch_bytes) {
     __syncwarp();
     const int sub = c.lane >> 3, k = c.lane & 7;
+    uint4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = i * 4 + sub;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (row < c.nvalid) v = *reinterpret_cast<const uint4*>(g0 + row * pitch_bytes + (k << 4));
-        *reinterpret_cast<uint4*>(c.sb + row * 128 + ((k ^ (row & 7)) << 4)) = v;
+        v[i] = make_uint4(0, 0, 0, 0);
+        if (row < c.nvalid) v[i] = *reinterpret_cast<const uint4*>(g0 + row * pitch_bytes + (k << 4));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + sub;
+        sts128(c.sb + row * 128 + ((k ^ (row & 7)) << 4), v[i]);
     }
     __syncwarp();
 #pragma unroll
-    for (int k2 = 0; k2 < 8; ++k2)
-        regs[k2] = *reinterpret_cast<const uint4*>(c.sb + c.lane * 128 + ((k2 ^ (c.lane & 7)) << 4));
+    for (int k2 = 0; k2 < 8; ++k2) regs[k2] = lds128(c.sb + c.lane * 128 + ((k2 ^ (c.lane & 7)) << 4));
 }
 
 // W fp32 outputs of this thread's row (W = 32, or 16 after GLU) at output column n -> fp32 C and/or (h,l) pair
-template <int W>
+template <int W, bool BIG>
 __device__ __forceinline__ void emit(const TcParams& p, const EpiCtx& c, const float (&o)[W], int n, int n_limit) {
     const bool full = n + W - 1 < n_limit;
     const bool row_ok = c.lane < c.nvalid;
     const int64_t my_row = c.row0 + c.lane;
     if (p.C) {
         if ((p.flags & 1) && full && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
-            uint4 regs[W / 4];
+            constexpr int CH = (W == 32 && !BIG) ? 4 : W / 4;     // 2 KB staging: a 32-wide fp32 block goes in two halves
 #pragma unroll
-            for (int j = 0; j < W / 4; ++j)
-                regs[j] = make_uint4(__float_as_uint(o[4 * j]), __float_as_uint(o[4 * j + 1]), __float_as_uint(o[4 * j + 2]),
-                                     __float_as_uint(o[4 * j + 3]));
-            staged_store<W / 4>(c, regs, reinterpret_cast<uint8_t*>(p.C + c.row0 * p.ldc + n), p.ldc * 4);
+            for (int part = 0; part < (W / 4) / CH; ++part) {
+                uint4 regs[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int e = (part * CH + j) * 4;
+                    regs[j] = make_uint4(__float_as_uint(o[e]), __float_as_uint(o[e + 1]), __float_as_uint(o[e + 2]), __float_as_uint(o[e + 3]));
+                }
+                staged_store<CH>(c, regs, reinterpret_cast<uint8_t*>(p.C + c.row0 * p.ldc + n + part * CH * 4), p.ldc * 4);
+            }
         } else if (row_ok && full && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
             float* cp = p.C + my_row * p.ldc + n;
 #pragma unroll
@@ -277,6 +301,7 @@ __device__ __forceinline__ void emit(const TcParams& p, const EpiCtx& c, const f
 
 // One 32-column slice of a finished output row: bias was already added; apply the epilogue and store.
 // `n` is the global column of v[0] (warp-uniform).
+template <bool BIG>
 __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, float (&v)[32], int n) {
     if (p.epi == MASR_EPI_BIAS_GLU) {
         // interleaved (value, gate) columns -> 16 outputs at column n/2 of an N/2-wide output
@@ -291,7 +316,7 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[j + k] = v[2 * (j + k)] * e[k];
         }
-        emit<16>(p, c, o, n >> 1, p.N >> 1);
+        emit<16, BIG>(p, c, o, n >> 1, p.N >> 1);
         return;
     }
     switch (p.epi) {
@@ -318,7 +343,7 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
             break;
         case MASR_EPI_RESIDUAL: {
             const bool vec_r = (p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
-            if ((p.flags & 2) && n + 31 < p.N && vec_r) {
+            if (BIG && (p.flags & 2) && n + 31 < p.N && vec_r) {
                 uint4 rr[8];
                 staged_load(c, rr, reinterpret_cast<const uint8_t*>(p.residual + c.row0 * p.ldr + n), p.ldr * 4);
 #pragma unroll
@@ -346,7 +371,7 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
         }
         default: break;
     }
-    emit<32>(p, c, v, n, p.N);
+    emit<32, BIG>(p, c, v, n, p.N);
 }
 
 // Accumulation: the tensor core adds into its fp32 TMEM accumulator with truncation, so a long K loop
@@ -358,13 +383,13 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  TMEM holds
 // main[2] (ping-pong by chunk) and corr[2] (ping-pong by tile) = 512 columns, so the MMA warp runs tile
 // i+1 while the 8 epilogue warps finish tile i.
-template <bool CONV>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool CONV, int EW>
+__global__ void __launch_bounds__(tc_threads(EW), 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, int tiles_n, int tiles_t) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi_stage = smem + TSTAGES * STAGE_BYTES;                // EPI_WARPS x 4 KB (see staged_store)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_WARPS * EPI_STAGE_BYTES);
+    uint8_t* epi_stage = smem + TSTAGES * STAGE_BYTES;                // EPI_STAGE_TOTAL / EW per warp (see staged_store)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_TOTAL);
     uint64_t* empty_bar = full_bar + TSTAGES;
     uint64_t* main_full = empty_bar + TSTAGES;     // [2]
     uint64_t* main_empty = main_full + 2;          // [2]
@@ -379,8 +404,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
         tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]); tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
         for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], EPI_WARPS);
-            mbar_init(&corr_full[s], 1); mbar_init(&corr_empty[s], EPI_WARPS);
+            mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], EW);
+            mbar_init(&corr_full[s], 1); mbar_init(&corr_empty[s], EW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -466,24 +491,27 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             }
         }
     } else {
-        // ---- 8 epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----
-        const int q = warp & 3, half = (warp - 2) >> 2;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)half * (TBN / 2);
+        // ---- EW epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4 (CW columns each) ----
+        constexpr int CW = TBN / (EW / 4);                             // 64 columns per warp (EW = 8) or 32 (EW = 16)
+        constexpr int NCH = CW / 32;                                   // 32-column chunks per warp
+        constexpr bool BIG = (EPI_STAGE_TOTAL / EW) >= 4096;
+        const int q = warp & 3, cgrp = (warp - 2) >> 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cgrp * CW;
         const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
         EpiCtx ctx;
-        ctx.sb = epi_stage + (warp - 2) * EPI_STAGE_BYTES;
+        ctx.sb = smem_u32(epi_stage) + (warp - 2) * (EPI_STAGE_TOTAL / EW);
         ctx.lane = lane;
         uint32_t cg = 0, tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             int n0, m0, t0, b;
             decode(tile, n0, m0, t0, b);
-            const int nw = n0 + half * (TBN / 2);                      // first column of this warp
-            // bias of the warp's 64 columns: lane l keeps columns l and 32+l, broadcast by shuffle below;
+            const int nw = n0 + cgrp * CW;                             // first column of this warp
+            // bias of the warp's columns: lane l keeps columns l (and 32+l), broadcast by shuffle below;
             // fetched before the accumulator wait so its latency is hidden
             float bias0 = 0.f, bias1 = 0.f;
             if (p.bias != nullptr) {
                 if (nw + lane < p.N) bias0 = __ldg(p.bias + nw + lane);
-                if (nw + 32 + lane < p.N) bias1 = __ldg(p.bias + nw + 32 + lane);
+                if (NCH > 1 && nw + 32 + lane < p.N) bias1 = __ldg(p.bias + nw + 32 + lane);
             }
             // row mapping: the warp's 32 tile rows are 32 consecutive output rows in both modes
             if (CONV) {
@@ -502,12 +530,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
                 mbar_wait(&corr_full[tl & 1], (tl >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < TBN / 64; ++cc) {
+                for (int cc = 0; cc < NCH; ++cc) {
                     uint32_t r[32], rc[32];
                     tmem_ld32(lane_base + (cg & 1) * TBN + cc * 32, r);
                     tmem_ld32(lane_base + 2 * TBN + (tl & 1) * TBN + cc * 32, rc);
                     tmem_ld_wait();
-                    if (cc == TBN / 64 - 1) {                          // TMEM released: the rest runs from registers
+                    if (cc == NCH - 1) {                          // TMEM released: the rest runs from registers
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) { mbar_arrive(&main_empty[cg & 1]); mbar_arrive(&corr_empty[tl & 1]); }
@@ -519,19 +547,19 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         v[j] = fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])) + __shfl_sync(0xffffffffu, bsrc, j);
-                    store_chunk(p, ctx, v, n);
+                    store_chunk<BIG>(p, ctx, v, n);
                 }
                 ++cg;
                 continue;
             }
-            float acc[TBN / 2];
+            float acc[CW];
 #pragma unroll
-            for (int j = 0; j < TBN / 2; ++j) acc[j] = 0.f;
+            for (int j = 0; j < CW; ++j) acc[j] = 0.f;
             for (int c = 0; c < nchunks; ++c, ++cg) {
                 mbar_wait(&main_full[cg & 1], (cg >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < TBN / 64; ++cc) {
+                for (int cc = 0; cc < NCH; ++cc) {
                     uint32_t r[32];
                     tmem_ld32(lane_base + (cg & 1) * TBN + cc * 32, r);
                     tmem_ld_wait();
@@ -545,7 +573,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             mbar_wait(&corr_full[tl & 1], (tl >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int cc = 0; cc < TBN / 64; ++cc) {
+            for (int cc = 0; cc < NCH; ++cc) {
                 uint32_t rc[32];
                 tmem_ld32(lane_base + 2 * TBN + (tl & 1) * TBN + cc * 32, rc);
                 tmem_ld_wait();
@@ -556,14 +584,14 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             __syncwarp();
             if (lane == 0) mbar_arrive(&corr_empty[tl & 1]);           // TMEM released: the rest runs from registers
 #pragma unroll
-            for (int cc = 0; cc < TBN / 64; ++cc) {
+            for (int cc = 0; cc < NCH; ++cc) {
                 const int n = nw + cc * 32;
                 if (n >= p.N) break;                                   // warp-uniform
                 float v[32];
                 const float bsrc = cc ? bias1 : bias0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = acc[cc * 32 + j] + __shfl_sync(0xffffffffu, bsrc, j);
-                store_chunk(p, ctx, v, n);
+                store_chunk<BIG>(p, ctx, v, n);
             }
         }
     }
@@ -576,7 +604,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     }
 }
 
-constexpr size_t kTcSmem = TSTAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + tmem slot*/;
+constexpr size_t kTcSmem = TSTAGES * STAGE_BYTES + EPI_STAGE_TOTAL + 1024 /*align*/ + 256 /*barriers + tmem slot*/;
 static_assert(kTcSmem <= 232448, "tc_gemm shared memory exceeds the 227 KB per-CTA limit of sm_100");
 
 // ---- fp32 -> (h,l) split, elementwise (weights at load time; activations produced by SIMT kernels) ----
@@ -644,12 +672,13 @@ static int make_map_plane(CUtensorMap* map, const void* ptr, int B, int TH, int 
     return MASR_OK;
 }
 
-// Epilogue flags.  Default 1 = staged (row-contiguous) stores: measured on B200 (tools/gemm_bench.py, M=7936)
-// ffn_w1 58.5 -> 42.1 us, qkv 35.5 -> 23.5 us, ctc head 91 -> 63 us; staging the residual READ as well (bit 1)
-// did not pay (w_2 31 -> 35 us).  MASR_TC_FLAGS overrides for A/B runs.
+// Kernel-variant flags, MASR_TC_FLAGS overrides for A/B runs (tools/gemm_bench.py; B200, M = 7936):
+//   bit 0  staged (row-contiguous) epilogue stores      ffn_w1 58.5 -> 42.1 us, qkv 35.5 -> 23.5, ctc head 91 -> 63
+//   bit 1  stage the residual READ as well              did not pay (w_2 31 -> 35 us); off
+//   bit 2  16 epilogue warps x 32 columns instead of 8 x 64   ffn_w1 43.1 -> 35.0 us, step 4.88 -> 4.59 ms
 static int tc_flags() {
     const char* e = getenv("MASR_TC_FLAGS");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 5;
 }
 
 static int num_sms() {
@@ -670,8 +699,10 @@ static int ensure_tc_attrs() {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!g_tc_attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
         if (e != cudaSuccess) { set_last_error("tc_gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         g_tc_attr_set[dev] = true;
     }
@@ -707,7 +738,8 @@ extern "C" int masr_conv2_tc_f16x2(const void* c1h, const void* c1l, const void*
     const int tiles_n = (C + TBN - 1) / TBN, tiles_t = (T2 + CONV_TR - 1) / CONV_TR;
     const int num_tiles = tiles_n * tiles_t * B;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    tc_gemm_kernel<true><<<grid, TC_THREADS, kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t);
+    if (p.flags & 4) tc_gemm_kernel<true, 16><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t);
+    else tc_gemm_kernel<true, 8><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t);
     return check_launch("tc_gemm_kernel<conv>");
 }
 
@@ -746,6 +778,7 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = tiles_n * tiles_m;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    tc_gemm_kernel<false><<<grid, TC_THREADS, kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1);
+    if (p.flags & 4) tc_gemm_kernel<false, 16><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1);
+    else tc_gemm_kernel<false, 8><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1);
     return check_launch("tc_gemm_kernel");
 }
