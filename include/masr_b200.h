@@ -55,6 +55,13 @@ int masr_check_device(void);
 
 /* ---- audio front-end -------------------------------------------------------------------------- */
 
+/* Host-side staging of a batch: copy B separate float32 host arrays (what MASRPredictor.predict receives one at a
+ * time, masr/predict.py:147-164; waves[b] has lengths[b] samples) back to back into the page-locked buffer `pinned`
+ * and from there to `dev` (both sum(lengths) floats), packing on up to `nthreads` host threads and issuing each part's
+ * cudaMemcpyAsync on `stream` as soon as it is packed.  Returns once the last copy has been issued. */
+int masr_stage_waves_f32(const void* const* waves, const int64_t* lengths, int B, float* pinned, float* dev, int nthreads,
+                         void* stream);
+
 /* Bytes of scratch masr_wave_gain_f32 needs for B utterances of at most max_samples samples. */
 int masr_fbank_workspace_bytes(int B, int64_t max_samples, int64_t* bytes_host);
 

@@ -22,6 +22,7 @@ _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "masr_abi_version": [],
     "masr_check_device": [],
+    "masr_stage_waves_f32": [_vp, _vp, _i, _vp, _vp, _i, _vp],
     "masr_fbank_workspace_bytes": [_i, _i64, C.POINTER(_i64)],
     "masr_wave_gain_f32": [_vp, _vp, _i, _i64, _f, _f, _vp, _vp, _vp, _vp],
     "masr_fbank_f32": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],

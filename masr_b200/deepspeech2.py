@@ -140,11 +140,8 @@ class DeepSpeech2Engine(ConformerEngine):
             "logits": torch.empty(M, self.Vpad, device=dev, dtype=f32),
             "ids": torch.empty(M, device=dev, dtype=torch.int32),
             "maxp": torch.empty(M, device=dev, dtype=f32),
-            "tokens": torch.empty(B, max(1, T), device=dev, dtype=torch.int32),
-            "ntok": torch.empty(B, device=dev, dtype=torch.int32),
-            "psum": torch.empty(B, device=dev, dtype=f32),
-            "pcount": torch.empty(B, device=dev, dtype=torch.int32),
         }
+        self._alloc_out_pack(ws, B, T)
         ws["t0p"] = ws["xp"]
         if len(self._ws) > 8:
             self._ws.clear()

@@ -81,6 +81,7 @@ class ConformerEngine:
         self._ws: Dict[Tuple, Dict[str, torch.Tensor]] = {}
         self.launches = 0
         self._pinned: Optional[torch.Tensor] = None      # grow-only pinned staging buffer for H2D copies
+        self._out_pinned: Optional[torch.Tensor] = None  # pinned landing buffer of the packed per-step outputs
         self._staged: Optional[torch.cuda.Event] = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -216,11 +217,8 @@ class ConformerEngine:
             "logits": torch.empty(max(1, M), self.Vpad, device=dev, dtype=f32),
             "ids": torch.empty(max(1, M), device=dev, dtype=torch.int32),
             "maxp": torch.empty(max(1, M), device=dev, dtype=f32),
-            "tokens": torch.empty(B, max(1, T), device=dev, dtype=torch.int32),
-            "ntok": torch.empty(B, device=dev, dtype=torch.int32),
-            "psum": torch.empty(B, device=dev, dtype=f32),
-            "pcount": torch.empty(B, device=dev, dtype=torch.int32),
         }
+        self._alloc_out_pack(ws, B, T)
         if self.gemm_path == "tc":
             f16 = torch.float16
             TH = (F1 + 1) // 2
@@ -237,10 +235,23 @@ class ConformerEngine:
         self._ws[key] = ws
         return ws
 
+    def _alloc_out_pack(self, ws, B: int, T: int):
+        """Everything that goes back to the host lives in ONE buffer (a single D2H copy per step):
+        tokens int32[B, T] | ntok int32[B] | pcount int32[B] | status int32[B] | psum f32[B]."""
+        Tt = max(1, T)
+        pack = torch.zeros(B * Tt + 4 * B, device=self.device, dtype=torch.int32)
+        ws["out_pack"] = pack
+        ws["tokens"] = pack[:B * Tt].view(B, Tt)
+        ws["ntok"] = pack[B * Tt:B * Tt + B]
+        ws["pcount"] = pack[B * Tt + B:B * Tt + 2 * B]
+        ws["status"] = pack[B * Tt + 2 * B:B * Tt + 3 * B]
+        ws["psum"] = pack[B * Tt + 3 * B:].view(torch.float32)
+
     # ---- front-end ---------------------------------------------------------------------------
     def fbank(self, waves: Sequence[np.ndarray], use_db_normalization: bool = True, target_db: float = -20.0,
               wave_dev: Optional[torch.Tensor] = None, offsets_dev: Optional[torch.Tensor] = None,
-              lengths: Optional[Sequence[int]] = None, force_fmax: Optional[int] = None):
+              lengths: Optional[Sequence[int]] = None, force_fmax: Optional[int] = None,
+              status_out: Optional[torch.Tensor] = None):
         """float32 waveforms in [-1,1) -> (feats [B,Fmax,80] on device, frame counts, status flags).
 
         Either host arrays (copied through pinned memory) or an already packed device buffer
@@ -275,7 +286,11 @@ class ConformerEngine:
         max_samples = max(lengths) if lengths else 0
         dev = self.device
         feats = torch.empty(B, max(1, Fmax), NUM_MEL, device=dev, dtype=torch.float32)
-        status = torch.zeros(B, device=dev, dtype=torch.int32)
+        if status_out is not None:
+            status = status_out
+            status.zero_()
+        else:
+            status = torch.zeros(B, device=dev, dtype=torch.int32)
         gain = None
         self.last_gain = None
         if use_db_normalization:
@@ -466,6 +481,7 @@ class ConformerEngine:
 
     # ---- CUDA-graph replay of the device step (launch-bound otherwise: ~190 launches per step) ------------
     GRAPH_FRAME_QUANTUM = 32      # Fmax is rounded up so ragged batches share graphs; padding never changes results
+    STAGE_THREADS = 8             # host threads packing the pinned staging buffer (csrc/stage.cu)
 
     def _graph_for(self, B: int, Fpad: int, use_db: bool, target_db: float):
         key = (B, Fpad, use_db, float(target_db))
@@ -485,8 +501,9 @@ class ConformerEngine:
         frames = [Fpad] * B
 
         def body():
+            ws0 = self._workspace(B, Fpad)
             feats, _, status = self.fbank(None, use_db, target_db, wave_dev=g["wave"], offsets_dev=g["offs"],
-                                          lengths=lengths, force_fmax=Fpad)
+                                          lengths=lengths, force_fmax=Fpad, status_out=ws0["status"])
             enc, tl, T, ws = self.encode(feats, frames, tlens_dev=g["tlens"])
             self.ctc_greedy(enc, tl, T, ws)
             return ws, status, T
@@ -547,7 +564,8 @@ class ConformerEngine:
         if max(tl) == 0:
             return GreedyResult([[] for _ in range(B)], [0.0] * B, None, np.zeros(B, np.int32), np.zeros(B, np.int32))
         g = self._graph_for(B, Fpad, use_db, target_db)
-        # stage inputs: packed samples + offsets + lengths through the pinned buffer, three async H2D copies
+        # stage inputs: the native stager packs the utterances into the pinned buffer on a few host threads and issues the
+        # H2D copy of every finished part at once (csrc/stage.cu); offsets + lengths follow as two tiny copies
         offs = np.zeros(B + 1, np.int64)
         np.cumsum(lengths, out=offs[1:])
         total = int(offs[-1])
@@ -556,15 +574,16 @@ class ConformerEngine:
         need = total + 4 * (B + 2) + 8
         if self._pinned is None or self._pinned.numel() < need:
             self._pinned = torch.empty((int(1.25 * need) + 1024) // 2 * 2, dtype=torch.float32, pin_memory=True)
-        hv = self._pinned.numpy()
-        for i, w in enumerate(waves):
-            hv[offs[i]:offs[i + 1]] = w
+        waves = [w if (w.dtype == np.float32 and w.flags.c_contiguous) else np.ascontiguousarray(w, np.float32) for w in waves]
+        ptrs = (_lib.C.c_void_p * B)(*[w.ctypes.data for w in waves])
+        lens_c = (_lib.C.c_int64 * B)(*lengths)
+        call("masr_stage_waves_f32", ptrs, lens_c, B, self._pinned.data_ptr(), g["wave"].data_ptr(), self.STAGE_THREADS,
+             self._stream())
         t0 = (total + 1) // 2 * 2
         po = self._pinned[t0:t0 + 2 * (B + 1)].view(torch.int64)
-        po.copy_(torch.from_numpy(offs))
+        po.numpy()[:] = offs
         pt = self._pinned[t0 + 2 * (B + 1):t0 + 2 * (B + 1) + B].view(torch.int32)
-        pt.copy_(torch.tensor(tl1, dtype=torch.int32))
-        g["wave"][:total].copy_(self._pinned[:total], non_blocking=True)
+        pt.numpy()[:] = tl1
         g["offs"].copy_(po, non_blocking=True)
         g["tlens"].copy_(pt, non_blocking=True)
         self._staged = torch.cuda.Event()
@@ -573,12 +592,21 @@ class ConformerEngine:
         g["graph"].replay()
         self.launches += g["launches"]
         ws = g["ws"]
-        tok = ws["tokens"].cpu().numpy()
-        ntok = ws["ntok"].cpu().numpy()
-        psum = ws["psum"].cpu().numpy()
-        pcnt = ws["pcount"].cpu().numpy()
-        st_h = g["status"].cpu().numpy()
-        self.d2h_bytes += tok.nbytes + ntok.nbytes + psum.nbytes + pcnt.nbytes + st_h.nbytes
+        # one D2H copy of the packed outputs (tokens | ntok | pcount | status | psum) into pinned memory
+        pack = ws["out_pack"]
+        if self._out_pinned is None or self._out_pinned.numel() < pack.numel():
+            self._out_pinned = torch.empty(max(4096, 2 * pack.numel()), dtype=torch.int32, pin_memory=True)
+        oh = self._out_pinned[:pack.numel()]
+        oh.copy_(pack, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        on = oh.numpy()
+        Tt = ws["tokens"].shape[1]
+        tok = on[:B * Tt].reshape(B, Tt)
+        ntok = on[B * Tt:B * Tt + B]
+        pcnt = on[B * Tt + B:B * Tt + 2 * B]
+        st_h = on[B * Tt + 2 * B:B * Tt + 3 * B].copy()
+        psum = on[B * Tt + 3 * B:B * Tt + 4 * B].view(np.float32)
+        self.d2h_bytes += on.nbytes
         tokens = [tok[b, :ntok[b]].tolist() for b in range(B)]
         scores = [greedy_score(psum[b], pcnt[b]) for b in range(B)]
         fid = ws["ids"][:B * T].view(B, T).cpu().numpy() if return_frames else None

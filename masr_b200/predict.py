@@ -112,7 +112,7 @@ class MASRPredictor:
             raise Exception(f"masr_b200: model '{self.configs.use_model}' is not implemented yet "
                             f"(available: {sorted(engines)})")
         self.predictor = engines[self.configs.use_model](model_path, streaming=bool(self.configs.streaming))
-        self._can_stream = self.configs.use_model in ('conformer', 'deepspeech2')
+        self._can_stream = self.configs.use_model in ('conformer', 'deepspeech2', 'squeezeformer')
         if self.predictor.V != self._text_featurizer.vocab_size:
             raise Exception(f"vocabulary has {self._text_featurizer.vocab_size} entries but the model's CTC head has "
                             f"{self.predictor.V}")

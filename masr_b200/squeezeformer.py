@@ -179,11 +179,17 @@ class SqueezeformerEngine(ConformerEngine):
             t[i, "pw1"], t[i, "pw2"] = self._split(L.pw1), self._split(L.pw2)
         torch.cuda.synchronize(self.device)
 
-    def new_stream(self):
-        raise NotImplementedError("chunk (streaming) decoding is implemented for the Conformer only so far")
+    def new_stream(self, max_frames: int = 3000):
+        """Streaming state of one utterance (``InferencePredictor`` att/cnn caches + offset): a one-slot stream pool."""
+        from .stream_pool import PoolStream, SqueezeformerStreamPool
+        return PoolStream(SqueezeformerStreamPool(self, 1, max_frames))
 
-    def encode_chunk(self, *a, **k):
-        raise NotImplementedError("chunk (streaming) decoding is implemented for the Conformer only so far")
+    def encode_chunk(self, feats_chunk, st, required_cache_size: int = -1, want_probs: bool = False):
+        """``SqueezeformerModel.get_encoder_out_chunk`` for one stream (encoder.py:240-361): feats_chunk [n<=67, 80] on device
+        -> (ids, max-prob) device tensors of length ((n-1)//2-1)//2."""
+        if want_probs:
+            raise NotImplementedError("posteriors of the chunk path are not exposed for this model")
+        return st.encode_chunk(feats_chunk, required_cache_size)
 
     def _ln_ada(self, x, gb, y, ada, yp, M):
         self._k("layernorm", "masr_layernorm_ada_split_f16", _p(x), self.d, _p(gb[0]), _p(gb[1]), _p(y),

@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import EPI_BIAS_GLU, EPI_BIAS_SCALE, EPI_BIAS_SILU, EPI_RESIDUAL
+from ._lib import EPI_BIAS, EPI_BIAS_GLU, EPI_BIAS_SCALE, EPI_BIAS_SILU, EPI_RESIDUAL
 from .audio import pcm_bytes_to_float32, samples_to_float32
 from .engine import ConformerEngine, _p, greedy_score, subsampled_len
 from .predict import CACHED_FEATURE_NUM, DECODING_WINDOW, FRAME_SHIFT, chunk_starts
@@ -140,13 +140,205 @@ class ConformerStreamPool:
         return b["ids"].view(S, C), b["maxp"].view(S, C), tout
 
 
+class SqueezeformerStreamPool:
+    """``ConformerStreamPool`` for the streaming Squeezeformer (``SqueezeformerEncoder.forward_chunk``,
+    masr/model_utils/squeezeformer/encoder.py:240-361, with ``required_cache_size < 0`` as ``predict_stream`` passes).
+
+    Blocks 5..10 run at half the frame rate: 16 chunk frames -> 8 (``TimeReductionLayerStream``: kernel 1, stride 2), and
+    their K|V caches are kept at that rate (the reference stores them ``repeat_interleave``d to the full rate and reads them
+    back with ``[::2]``, :339-356 — a round trip).  The conv-module left context (30 rows of the ada-scaled input,
+    convolution.py:119-127) is kept as the fp16 (h,l) operand pair the pointwise GEMM consumes.  A chunk shorter than 67
+    frames (the last one of a stream) is supported once per stream: afterwards the slot must be reset."""
+
+    def __init__(self, eng, n_slots: int, max_frames: int = 3000):
+        if not eng.causal:
+            raise Exception("chunk decoding needs a streaming (causal) model")
+        self.eng, self.S = eng, n_slots
+        self.cap = (max_frames + 15) // 16 * 16
+        self.cap2 = self.cap // 2
+        dev, d, w = eng.device, eng.d, eng.w
+        f16, f32 = torch.float16, torch.float32
+        nl = len(w.layers)
+        S, C = n_slots, CHUNK_OUT
+        C2 = C // 2
+        self.lorder = w.kernel - 1
+        F1 = (CHUNK_FRAMES - 1) // 2
+        TH = (F1 + 1) // 2
+        M = S * C
+        LC = self.lorder + C
+        self.reduced = [eng.REDUCE <= i < eng.RECOVER for i in range(nl)]
+        self.kv = [(torch.zeros(S * (self.cap2 if r else self.cap), 2 * d, device=dev, dtype=f16),
+                    torch.zeros(S * (self.cap2 if r else self.cap), 2 * d, device=dev, dtype=f16)) for r in self.reduced]
+        # [cache ++ chunk] input rows of every block's conv module, as fp16 pairs
+        self.xcat = [(torch.zeros(S, self.lorder + (C2 if r else C), d, device=dev, dtype=f16),
+                      torch.zeros(S, self.lorder + (C2 if r else C), d, device=dev, dtype=f16)) for r in self.reduced]
+        self.lens_host = [0] * S
+        self.b = {
+            "c1p": (torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16), torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16)),
+            "c2p": (torch.empty(M * eng.f2, d, device=dev, dtype=f16), torch.empty(M * eng.f2, d, device=dev, dtype=f16)),
+            "x": torch.zeros(M, d, device=dev, dtype=f32), "y": torch.zeros(M, d, device=dev, dtype=f32),
+            "saved": torch.zeros(M, d, device=dev, dtype=f32),
+            "t0p": (torch.zeros(M, d, device=dev, dtype=f16), torch.zeros(M, d, device=dev, dtype=f16)),
+            "t1p": (torch.zeros(M, d, device=dev, dtype=f16), torch.zeros(M, d, device=dev, dtype=f16)),
+            "hidp": (torch.empty(M, w.ffn, device=dev, dtype=f16), torch.empty(M, w.ffn, device=dev, dtype=f16)),
+            "qkv": torch.zeros(M, 3 * d, device=dev, dtype=f32),
+            "qkvp": (torch.zeros(M, 3 * d, device=dev, dtype=f16), torch.zeros(M, 3 * d, device=dev, dtype=f16)),
+            "g": torch.empty(S * LC, d, device=dev, dtype=f32),
+            "logits": torch.empty(M, eng.Vpad, device=dev, dtype=f32),
+            "ids": torch.empty(M, device=dev, dtype=torch.int32), "maxp": torch.empty(M, device=dev, dtype=f32),
+            "qlen": torch.zeros(S, device=dev, dtype=torch.int32), "klen": torch.zeros(S, device=dev, dtype=torch.int32),
+            "qlen2": torch.zeros(S, device=dev, dtype=torch.int32), "klen2": torch.zeros(S, device=dev, dtype=torch.int32),
+            "clen": torch.full((S,), self.lorder + C, device=dev, dtype=torch.int32),
+            "clen2": torch.full((S,), self.lorder + C2, device=dev, dtype=torch.int32),
+        }
+
+    def reset(self, slot: int):
+        """``InferencePredictor.reset_stream`` for one slot (inference_predictor.py:97-102)."""
+        self.lens_host[slot] = 0
+        for xh, xl in self.xcat:
+            xh[slot].zero_()
+            xl[slot].zero_()
+
+    def step(self, feats: torch.Tensor, nframes: Sequence[int]):
+        """feats [S, 67, 80] raw log-mel (device), nframes[s] = valid feature frames of slot s this round (0 = idle).
+        -> (ids [S,16] int32, maxp [S,16], tout) — the first tout[s] = ((n-1)//2-1)//2 entries of row s are valid."""
+        eng, S, C = self.eng, self.S, CHUNK_OUT
+        C2 = C // 2
+        w, d, tw, b = eng.w, eng.d, eng._tcw, self.b
+        dev = eng.device
+        tout = [subsampled_len(int(n)) for n in nframes]
+        tout2 = [(t + 1) // 2 for t in tout]
+        for s in range(S):
+            if tout[s] and self.lens_host[s] % C:
+                raise AssertionError(f"stream slot {s}: a short (final) chunk was already decoded; reset the stream first")
+            if self.lens_host[s] + tout[s] > self.cap or self.lens_host[s] + tout[s] >= w.max_len:
+                raise AssertionError(f"stream slot {s}: {self.lens_host[s] + tout[s]} cached frames exceed the pool capacity")
+        b["qlen"].copy_(torch.tensor(tout, dtype=torch.int32))
+        b["klen"].copy_(torch.tensor([self.lens_host[s] + tout[s] for s in range(S)], dtype=torch.int32))
+        b["qlen2"].copy_(torch.tensor(tout2, dtype=torch.int32))
+        b["klen2"].copy_(torch.tensor([self.lens_host[s] // 2 + tout2[s] for s in range(S)], dtype=torch.int32))
+
+        def scatter(cap, base, cnt, stride):
+            rows = torch.tensor([s * cap + base[s] + t for s in range(S) for t in range(cnt[s])], dtype=torch.int64, device=dev)
+            src = torch.tensor([s * stride + t for s in range(S) for t in range(cnt[s])], dtype=torch.int64, device=dev)
+            return rows, src
+        sc_full = scatter(self.cap, self.lens_host, tout, C)
+        sc_half = scatter(self.cap2, [n // 2 for n in self.lens_host], tout2, C2)
+        M, M2 = S * C, S * C2
+        F1 = (CHUNK_FRAMES - 1) // 2
+        x, y, saved, t0p, t1p, hidp, qkv, qkvp, g = (b["x"], b["y"], b["saved"], b["t0p"], b["t1p"], b["hidp"], b["qkv"],
+                                                      b["qkvp"], b["g"])
+        eng._k("conv1", "masr_conv1_cmvn_relu_planes_f16", _p(feats), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w), _p(w.conv1_b),
+               _p(b["c1p"][0]), _p(b["c1p"][1]), S, CHUNK_FRAMES, w.idim, F1, eng.w1_cols, d)
+        eng._k("conv2", "masr_conv2_tc_f16x2", _p(b["c1p"][0]), _p(b["c1p"][1]), _p(tw["conv2"][0]), _p(tw["conv2"][1]), _p(w.conv2_b),
+               None, _p(b["c2p"][0]), _p(b["c2p"][1]), S, F1, C, d)
+        eng._tc(b["c2p"], eng.f2 * d, tw["embed"], w.embed_b, M, d, eng.f2 * d, EPI_BIAS, C=y, ldc=d)
+        eng._ln_ada(y, w.preln, x, w.layers[0].att_ada, t0p, M)
+        nl = len(w.layers)
+        Mi, Ci, qlen, klen, clen, sc, cap = M, C, b["qlen"], b["klen"], b["clen"], sc_full, self.cap
+        for i, L in enumerate(w.layers):
+            if i == eng.REDUCE:
+                saved.copy_(x)
+                eng._k("time_reduce", "masr_time_reduce_dw_split_f16", _p(x), C, _p(w.tr_dw), _p(w.tr_dw_b), _p(t1p[0]), _p(t1p[1]),
+                       C2, _p(b["qlen"]), S, C2, int(w.tr_dw.shape[1]), 0, d)
+                eng._tc(t1p, d, tw["tr_pw"], w.tr_pw_b, M2, d, d, EPI_BIAS, C=x, ldc=d)
+                eng._k("affine_split", "masr_affine_split_f16", _p(x), _p(L.att_ada[0]), _p(L.att_ada[1]), _p(t0p[0]), _p(t0p[1]), M2, d)
+                Mi, Ci, qlen, klen, clen, sc, cap = M2, C2, b["qlen2"], b["klen2"], b["clen2"], sc_half, self.cap2
+            if i == eng.RECOVER:
+                eng._k("affine_split", "masr_affine_split_f16", _p(x), None, None, _p(t1p[0]), _p(t1p[1]), M2, d)
+                eng._tc(t1p, d, tw["rec"], w.rec_b, M2, d, d, EPI_BIAS, C=y, ldc=d)
+                eng._k("upsample_add", "masr_upsample2_add_f32", _p(saved), _p(y), _p(x), C, C2, S, C, d)
+                Mi, Ci, qlen, klen, clen, sc, cap = M, C, b["qlen"], b["klen"], b["clen"], sc_full, self.cap
+                eng._k("affine_split", "masr_affine_split_f16", _p(x), _p(L.att_ada[0]), _p(L.att_ada[1]), _p(t0p[0]), _p(t0p[1]), Mi, d)
+            LCi = self.lorder + Ci
+            # MHA over [cache ++ chunk] keys
+            eng._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, Cp=qkvp, ldc=3 * d)
+            kvh, kvl = self.kv[i]
+            rows, src = sc
+            if rows.numel():
+                kvh.index_copy_(0, rows, qkvp[0][:Mi].index_select(0, src)[:, d:])
+                kvl.index_copy_(0, rows, qkvp[1][:Mi].index_select(0, src)[:, d:])
+            ph, pl, _ = eng._ptab_pair(L)
+            eng._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, Ci, kvh.data_ptr(), kvl.data_ptr(), kvh.data_ptr() + 2 * d,
+                   kvl.data_ptr() + 2 * d, 2 * d, cap, _p(ph), _p(pl), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), d, Ci,
+                   _p(qlen), _p(klen), S, eng.h, eng.dk, Ci)
+            eng._tc(t1p, d, tw[i, "wo"], L.bo, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=y, ldc=d)
+            eng._ln_ada(y, L.ln1, x, L.ffn1_ada, t0p, Mi)
+            eng._tc(t0p, d, tw[i, "f1a"], L.ffn1[1], Mi, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
+            eng._tc(hidp, w.ffn, tw[i, "f1b"], L.ffn1[3], Mi, d, w.ffn, EPI_RESIDUAL, 1.0, x, d, C=y, ldc=d)
+            eng._ln_ada(y, L.ln2, x, L.conv_ada, t0p, Mi)
+            # conv module over [cache ++ chunk] per slot
+            xh, xl = self.xcat[i]
+            xh[:, self.lorder:].copy_(t0p[0][:Mi].view(S, Ci, d))
+            xl[:, self.lorder:].copy_(t0p[1][:Mi].view(S, Ci, d))
+            eng._tc((xh, xl), d, tw[i, "pw1"], L.pw1_b, S * LCi, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d)
+            eng._k("dwconv_bn_silu", "masr_dwconv_bn_silu_f32", _p(g), d, LCi, _p(L.dw), _p(L.dw_b), _p(L.bn[0]), _p(L.bn[1]), None,
+                   None, _p(t1p[0]), _p(t1p[1]), d, Ci, _p(clen), S, d, L.kernel, 0, Ci)
+            # new left context = the last `lorder` VALID rows: rows [n, n + lorder) of [cache ++ chunk], n = valid chunk rows
+            cnt = tout if Ci == C else tout2
+            if all(t == Ci for t in cnt):
+                xh[:, :self.lorder].copy_(xh[:, Ci:Ci + self.lorder].clone())
+                xl[:, :self.lorder].copy_(xl[:, Ci:Ci + self.lorder].clone())
+            else:
+                for s in range(S):
+                    if cnt[s]:
+                        xh[s, :self.lorder].copy_(xh[s, cnt[s]:cnt[s] + self.lorder].clone())
+                        xl[s, :self.lorder].copy_(xl[s, cnt[s]:cnt[s] + self.lorder].clone())
+            eng._tc(t1p, d, tw[i, "pw2"], L.pw2_b, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=y, ldc=d)
+            eng._ln_ada(y, L.ln3, x, L.ffn2_ada, t0p, Mi)
+            eng._tc(t0p, d, tw[i, "f2a"], L.ffn2[1], Mi, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
+            eng._tc(hidp, w.ffn, tw[i, "f2b"], L.ffn2[3], Mi, d, w.ffn, EPI_RESIDUAL, 1.0, x, d, C=y, ldc=d)
+            nxt = w.layers[i + 1].att_ada if (i + 1 < nl and i + 1 not in (eng.REDUCE, eng.RECOVER)) else None
+            eng._ln_ada(y, L.ln4, x, nxt, t0p, Mi)       # last block: pair(x) feeds the CTC head
+        eng._tc(t0p, d, tw["ctc"], w.ctc_b, M, eng.V, d, C=b["logits"], ldc=eng.Vpad)
+        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
+        for s in range(S):
+            self.lens_host[s] += tout[s]
+        return b["ids"].view(S, C), b["maxp"].view(S, C), tout
+
+
+class PoolStream:
+    """One stream = a one-slot pool behind the single-stream interface ``MASRPredictor.predict_stream`` uses
+    (``eng.new_stream()`` / ``eng.encode_chunk(chunk, stream)``)."""
+
+    def __init__(self, pool):
+        self.pool = pool
+        self.batch = torch.zeros(1, CHUNK_FRAMES, 80, device=pool.eng.device, dtype=torch.float32)
+
+    def reset(self):
+        self.pool.reset(0)
+
+    def encode_chunk(self, feats_chunk: torch.Tensor, required_cache_size: int = -1):
+        if required_cache_size >= 0:
+            raise NotImplementedError("bounded attention caches (required_cache_size >= 0) are not implemented for this model; "
+                                      "predict_stream always asks for the whole history")
+        n = int(feats_chunk.shape[0])
+        if n > CHUNK_FRAMES:
+            raise ValueError(f"a chunk has at most {CHUNK_FRAMES} feature frames")
+        if subsampled_len(n) == 0:
+            return None
+        self.batch[0, :n].copy_(feats_chunk)
+        ids, maxp, tout = self.pool.step(self.batch, [n])
+        return ids[0, :tout[0]], maxp[0, :tout[0]], None
+
+
+def make_pool(eng, n_slots: int, max_frames: int = 3000):
+    """The batched chunk-decoding pool that matches the engine's model family."""
+    from .squeezeformer import SqueezeformerEngine
+    if isinstance(eng, SqueezeformerEngine):
+        return SqueezeformerStreamPool(eng, n_slots, max_frames)
+    if type(eng) is ConformerEngine:
+        return ConformerStreamPool(eng, n_slots, max_frames)
+    raise NotImplementedError(f"no stream pool for {type(eng).__name__}")
+
+
 class StreamPool:
     """`predict_stream` for many streams at once (same per-stream results as one ``MASRPredictor`` per stream)."""
 
     def __init__(self, eng: ConformerEngine, vocab: Sequence[str], n_slots: int, use_db_normalization: bool = True,
                  target_db: float = -20.0, max_frames: int = 3000):
         self.eng, self.vocab, self.S = eng, list(vocab), n_slots
-        self.pool = ConformerStreamPool(eng, n_slots, max_frames)
+        self.pool = make_pool(eng, n_slots, max_frames)
         self.use_db, self.target_db = use_db_normalization, target_db
         self.remained: List[Optional[np.ndarray]] = [None] * n_slots
         self.cached: List[Optional[torch.Tensor]] = [None] * n_slots

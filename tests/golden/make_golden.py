@@ -270,10 +270,58 @@ def gen_predictor(tmp):
     print("pushes", pushes)
 
 
+def build_reference_squeezeformer(tmp, streaming, wseed):
+    from masr.model_utils.squeezeformer.model import SqueezeformerModel
+    cfg = yaml.safe_load(open(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "squeezeformer.yml"), encoding="utf-8"))
+    mi = os.path.join(tmp, f"mean_istd_{wseed}.json")
+    synth.write_mean_istd(mi, wseed)
+    model = SqueezeformerModel(input_dim=80, vocab_size=V, mean_istd_path=mi, streaming=streaming,
+                               encoder_conf=cfg["encoder_conf"], decoder_conf=cfg["decoder_conf"], **cfg["model_conf"])
+    res = model.load_state_dict(synth.to_torch(synth.squeezeformer_state_dict(wseed, V, streaming=streaming)), strict=False)
+    assert not res.unexpected_keys and all(k.startswith("decoder.") for k in res.missing_keys)
+    return model.eval(), cfg, mi
+
+
+SQZ_STREAM_CASE = ("sqz_stream_speech_3p7s", 0, "speech", 31, 59200 + 123, 8000)  # weight seed, kind, audio seed, samples, push
+
+
+def gen_predictor_squeezeformer(tmp):
+    """The real ``MASRPredictor`` with the streaming Squeezeformer (greedy): whole utterance, PCM pushes (the last chunk is
+    short) and per-chunk frame ids of ``get_encoder_out_chunk``."""
+    from masr.predict import MASRPredictor
+    name, wseed, kind, aseed, n, push = SQZ_STREAM_CASE
+    model, cfg, mi = build_reference_squeezeformer(tmp, True, wseed)
+    mp = os.path.join(tmp, "inference_sqz.pt")
+    torch.jit.save(model.export(), mp)
+    vp = os.path.join(tmp, "vocabulary.txt")
+    synth.write_vocabulary(vp, V)
+    cfg["dataset_conf"]["dataset_vocab"] = vp
+    cfg["dataset_conf"]["mean_istd_path"] = mi
+    cfg["decoder"] = "ctc_greedy"
+    np.random.seed(0)
+    pred = MASRPredictor(configs=cfg, model_path=mp, use_gpu=False)
+    x = make_audio(kind, aseed, n)
+    whole = pred.predict(audio_data=x.copy())
+    pcm = (np.clip(x, -1, 1) * 32767).astype("<i2")
+    pushes = []
+    pred.reset_stream()
+    for s in range(0, len(pcm), push):
+        r = pred.predict_stream(audio_data=pcm[s:s + push].tobytes(), is_end=s + push >= len(pcm))
+        pushes.append(None if r is None else {"text": r["text"], "score": r["score"]})
+    pred.reset_stream()
+    data = {"name": name, "wseed": wseed, "kind": kind, "aseed": aseed, "samples": n, "push": push,
+            "whole": whole, "pushes_pcm": pushes}
+    with open(os.path.join(HERE, "predictor_golden_squeezeformer.json"), "w", encoding="utf-8") as f:
+        json.dump(data, f, ensure_ascii=False, indent=1)
+    print("squeezeformer predictor whole", whole)
+    print("pushes", pushes)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     with tempfile.TemporaryDirectory() as tmp:
-        which = sys.argv[1:] or ["fbank", "encoder", "predictor", "efficient", "squeezeformer", "deepspeech2"]
+        which = sys.argv[1:] or ["fbank", "encoder", "predictor", "efficient", "squeezeformer", "deepspeech2",
+                                  "predictor_squeezeformer"]
         if "deepspeech2" in which:
             gen_deepspeech2(tmp)
         if "squeezeformer" in which:
@@ -284,5 +332,7 @@ if __name__ == "__main__":
             gen_encoder(tmp)
         if "predictor" in which:
             gen_predictor(tmp)
+        if "predictor_squeezeformer" in which:
+            gen_predictor_squeezeformer(tmp)
         if "efficient" in which:
             gen_efficient(tmp)

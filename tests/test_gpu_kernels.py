@@ -197,3 +197,22 @@ def test_ctc_argmax_and_collapse(rt):
         for p in kept:
             acc = np.float32(acc + p)
         assert ps[b].item() == pytest.approx(float(acc), rel=0, abs=0)       # same left-to-right float32 sum
+
+
+@pytest.mark.parametrize("lens,threads", [([160000] * 32, 8), ([5, 0, 400001, 17, 262144, 1], 4), ([1000], 8), ([300000] * 3, 1)])
+def test_stage_waves(rt, lens, threads):
+    """masr_stage_waves_f32: separate host arrays -> pinned buffer -> device, bit-identical to a plain concatenate."""
+    import ctypes as C
+    rng = np.random.default_rng(len(lens))
+    waves = [rng.standard_normal(n).astype(np.float32) for n in lens]
+    total = sum(lens)
+    pinned = torch.empty(total + 16, dtype=torch.float32, pin_memory=True)
+    dev = torch.full((total + 16,), float("nan"), device=rt.dev)
+    ptrs = (C.c_void_p * len(lens))(*[w.ctypes.data for w in waves])
+    lc = (C.c_int64 * len(lens))(*lens)
+    rt.call("masr_stage_waves_f32", ptrs, lc, len(lens), pinned.data_ptr(), dev.data_ptr(), threads, rt.st())
+    torch.cuda.synchronize()
+    ref = np.concatenate(waves)
+    assert np.array_equal(dev[:total].cpu().numpy(), ref)
+    assert np.array_equal(pinned[:total].numpy(), ref)
+    assert torch.isnan(dev[total:]).all()

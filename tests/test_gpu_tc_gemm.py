@@ -49,7 +49,10 @@ def test_split_roundtrip(rt):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (200, 256, 256), (1000, 2048, 256), (777, 256, 2048),
-                                   (129, 4233, 256), (300, 256, 4864), (5, 768, 256)])
+                                   (129, 4233, 256), (300, 256, 4864), (5, 768, 256),
+                                   # A-resident variant (K == 256, N >= 512): multi-tile groups, ragged last group,
+                                   # several units per CTA (the resident A tile is reloaded)
+                                   (7936, 2048, 256), (2500, 1100, 256), (12800, 1024, 256)])
 def test_tc_gemm_fp32_grade(rt, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / math.sqrt(K)

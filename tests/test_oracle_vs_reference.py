@@ -63,3 +63,40 @@ def test_full_and_chunk_forward_match(ref_model):
             assert (pr - pm).abs().max().item() < 1e-6
             assert (att - st.att_cache).abs().max().item() < 1e-6
             assert (cnn - st.cnn_cache).abs().max().item() < 1e-6
+
+
+def test_squeezeformer_chunk_forward_matches():
+    """oracle/squeezeformer.get_encoder_out_chunk against the live reference's TorchScript-able chunk method, chunk by
+    chunk (probabilities and both caches), including a short final chunk."""
+    ref_shims.install()
+    import tempfile
+    import yaml
+    from masr.model_utils.squeezeformer.model import SqueezeformerModel
+    from oracle import squeezeformer as osq
+    cfg_y = yaml.safe_load(open(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "squeezeformer.yml"), encoding="utf-8"))
+    with tempfile.TemporaryDirectory() as tmp:
+        mi = os.path.join(tmp, "mi.json")
+        synth.write_mean_istd(mi, 0)
+        m = SqueezeformerModel(input_dim=80, vocab_size=synth.DEFAULT_VOCAB_SIZE, mean_istd_path=mi, streaming=True,
+                               encoder_conf=cfg_y["encoder_conf"], decoder_conf=cfg_y["decoder_conf"], **cfg_y["model_conf"]).eval()
+    sdn = synth.squeezeformer_state_dict(0, streaming=True)
+    m.load_state_dict(synth.to_torch(sdn), strict=False)
+    sd = synth.to_torch(sdn)
+    cfg = osq.SqueezeformerConfig(causal=True)
+    feat = torch.from_numpy(ob.featurize(make_audio("speech", 9, 16000 * 3 + 4000)))[None]
+    with torch.no_grad():
+        st = osq.ChunkState()
+        att = torch.zeros(0, 0, 0, 0)
+        cnn = torch.zeros(0, 0, 0, 0)
+        off = 0
+        nf = feat.shape[1]
+        for cur in range(0, nf - 7 + 1, 64):
+            ch = feat[:, cur:min(cur + 67, nf)]
+            pr, att, cnn = m.get_encoder_out_chunk(ch, off, -16, att, cnn)
+            off += pr.shape[1]
+            pm = osq.get_encoder_out_chunk(sd, cfg, ch, st, -16)
+            assert pr.shape == pm.shape
+            assert torch.equal(pr.argmax(-1), pm.argmax(-1))
+            assert (pr - pm).abs().max().item() < 5e-6          # fp32 summation-order noise (different operand strides)
+            assert att.shape == st.att_cache.shape and (att - st.att_cache).abs().max().item() < 2e-5
+            assert cnn.shape == st.cnn_cache.shape and (cnn - st.cnn_cache).abs().max().item() < 2e-5
