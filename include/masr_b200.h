@@ -131,6 +131,14 @@ int masr_layernorm_f32(const float* x, int64_t ldx, const float* gamma, const fl
 int masr_layernorm_split_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, void* yh, void* yl,
                              int64_t ldy, int M, int D, float eps, void* stream);
 
+/* Two LayerNorms back to back in one pass: y1 = LN(x; gamma1, beta1) as fp32 (row pitch ldx; may alias x), then
+ * LN(y1; gamma2, beta2) as fp32 y2 (optional) and as the fp16 pair (row pitch ldy) — `norm_final` of one encoder block
+ * followed by the next block's `norm_ff_macaron`, or by `after_norm` after the last block (conformer/encoder.py:161,106,342).
+ * Bit-identical to masr_layernorm_f32 followed by masr_layernorm_split_f16. */
+int masr_layernorm2_split_f16(const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* y1,
+                              const float* gamma2, const float* beta2, float* y2, void* yh, void* yl, int64_t ldy, int M,
+                              int D, float eps, void* stream);
+
 /* Squeezeformer helpers.
  *  masr_layernorm_ada_split_f16: y = LayerNorm(x) (optional fp32 copy) and the fp16 pair of ada_scale*y+ada_bias — the
  *    post-norm + adaptive scale of the next sub-module input (squeezeformer/encoder.py:412-463, positionwise.py:57-58);
@@ -195,6 +203,14 @@ int masr_dwconv_ln_silu_strided_f32(const float* g, int64_t ldg, int64_t g_bstri
 int masr_grouped_attention_f32(const float* Q, const float* K, const float* V, const float* P, int64_t ld, int64_t bstride,
                                const float* pos_u, const float* pos_v, float* O, void* Oh, void* Ol, const int* lens,
                                int B, int H, int d_k, int group, int max_t, void* stream);
+
+/* The same with a K|V cache (``forward`` with ``cache``, attention.py:151-158): q_lens[b] query frames at Q rows
+ * b*q_bstride.. (pitch ldq), k_lens[b] key/value frames = [cache ++ chunk] at K/V rows b*k_bstride.. (pitch ldk); P row j
+ * belongs to key j; queries are grouped from the first chunk frame, keys from key 0.  Outputs in Q's layout. */
+int masr_grouped_attention_cache_f32(const float* Q, int64_t ldq, int64_t q_bstride, const float* K, const float* V,
+                                     int64_t ldk, int64_t k_bstride, const float* P, const float* pos_u, const float* pos_v,
+                                     float* O, void* Oh, void* Ol, const int* q_lens, const int* k_lens, int B, int H,
+                                     int d_k, int group, int max_q, void* stream);
 
 /* AvgPool1d(2, 2, ceil_mode=True, count_include_pad=False) over time per utterance (efficient_conformer/encoder.py:
  * 173-175): y[b,t] = mean(x[b,2t], x[b,2t+1]) (single element at an odd tail), rows >= ceil(len/2) are 0. */

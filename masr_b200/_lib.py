@@ -35,6 +35,7 @@ SIGNATURES = {
     "masr_conv2_tc_f16x2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "masr_layernorm_f32": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
     "masr_layernorm_split_f16": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
+    "masr_layernorm2_split_f16": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
     "masr_layernorm_ada_split_f16": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
     "masr_affine_split_f16": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "masr_dwconv_bn_silu_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i, _i, _vp],
@@ -49,6 +50,8 @@ SIGNATURES = {
     "masr_dwconv_ln_silu_strided_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i,
                                         _i, _i, _i, _f, _vp],
     "masr_grouped_attention_f32": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "masr_grouped_attention_cache_f32": [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                         _i, _i, _vp],
     "masr_avgpool2_time_f32": [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _vp],
     "masr_lstm_step_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _vp],
     "masr_ctc_frame_argmax_f32": [_vp, _i64, _i, _i, _vp, _vp, _vp, _i64, _vp],

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int kc = nb * 8 + 2 * t + (j & 1);
-                float s = fmaf(sc[nb][j], kLoI, sm[nb][j]) * p.scale;
+                float s = fmaf(sc[nb][j], kLoI, sm[nb][j]) * p.scale;        // p.scale = log2(e) / sqrt(d_k): scores live in the log2 domain
                 s = kc < nk ? s : -INFINITY;
                 sm[nb][j] = s;
                 mt[j >> 1] = fmaxf(mt[j >> 1], s);
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
             mt[r] = fmaxf(mt[r], __shfl_xor_sync(0xffffffffu, mt[r], 1));
             mt[r] = fmaxf(mt[r], __shfl_xor_sync(0xffffffffu, mt[r], 2));
             const float m_new = fmaxf(m_row[r], mt[r]);
-            alpha[r] = expf(m_row[r] - m_new);
+            alpha[r] = ex2_approx(m_row[r] - m_new);
             m_row[r] = m_new;
         }
         uint32_t ph[2][4], pl[2][4];
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
             float pv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                pv[j] = expf(sm[nb][j] - m_row[j >> 1]);
+                pv[j] = ex2_approx(sm[nb][j] - m_row[j >> 1]);   // SFU ex2 (<= 2 ulp): the IEEE expf cost as much issue time as the MMAs
                 rs[j >> 1] += pv[j];
             }
             const __half2 h01 = __floats2half2_rn(pv[0], pv[1]), h23 = __floats2half2_rn(pv[2], pv[3]);
@@ -321,7 +321,7 @@ extern "C" int masr_relpos_attention_tc(const float* Q, int64_t ldq, int64_t q_b
     }
     AttnMmaParams p{Q, ldq, q_bstride, (const __half*)Kh, (const __half*)Kl, (const __half*)Vh, (const __half*)Vl, ldk, k_bstride,
                     (const __half*)Ph, (const __half*)Pl, ldp, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, ldo, o_bstride, q_lens,
-                    k_lens, 1.0f / sqrtf((float)d_k), max_q};
+                    k_lens, 1.4426950408889634f / sqrtf((float)d_k), max_q};
     dim3 grid((max_q + MQ - 1) / MQ, H, B);
     relpos_attention_mma_kernel<<<grid, 128, kAttnMmaSmem, (cudaStream_t)stream>>>(p);
     return check_launch("relpos_attention_mma_kernel");

@@ -49,6 +49,22 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// SiLU / sigmoid on the SFU (ex2.approx + rcp.approx, <= 2 ulp each; absolute error < 2e-7 on the outputs): the accurate
+// expf + IEEE divide cost ~50 instructions per element, which made the activation the largest part of the GEMM epilogues
+// and of the depthwise-conv kernel.  Inside the fp32-grade budget (tests/test_gpu_tc_gemm.py, tests/test_gpu_kernels.py).
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
+__device__ __forceinline__ float fast_silu(float x) { return x * fast_sigmoid(x); }
+
 // 128-bit streaming global accesses (guide: Guideline 13).
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

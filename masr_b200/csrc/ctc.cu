@@ -61,28 +61,56 @@ __global__ void __launch_bounds__(256) ctc_frame_argmax_kernel(const float* __re
     }
 }
 
-// One thread per utterance: sequential scan (T <= a few thousand frames; latency-trivial).
-__global__ void ctc_greedy_collapse_kernel(const int* __restrict__ ids, const float* __restrict__ maxp, int64_t bstride,
-                                           const int* __restrict__ lens, int B, int blank, int prev_id_in,
-                                           int* __restrict__ tokens, int64_t tok_stride, int* __restrict__ ntok,
-                                           float* __restrict__ psum, int* __restrict__ pcount) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// One CTA per utterance.  Frames are staged through shared memory in tiles of 256 (coalesced loads); the keep flags
+// (id != blank and id != previous id) are compacted with warp ballots; the score sum stays a left-to-right float32 chain
+// over the non-blank frames, as `greedy_decoder` computes it (ctc_greedy_decoder.py:28-30), run by one thread from shared
+// memory.  (The first version walked global memory from one thread per utterance: 46 us of pure load latency.)
+__global__ void __launch_bounds__(256) ctc_greedy_collapse_kernel(const int* __restrict__ ids, const float* __restrict__ maxp,
+                                                                  int64_t bstride, const int* __restrict__ lens, int blank,
+                                                                  int prev_id_in, int* __restrict__ tokens, int64_t tok_stride,
+                                                                  int* __restrict__ ntok, float* __restrict__ psum,
+                                                                  int* __restrict__ pcount) {
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = lens[b];
     const int* id = ids + (int64_t)b * bstride;
     const float* mp = maxp + (int64_t)b * bstride;
     int* tk = tokens + (int64_t)b * tok_stride;
-    int prev = prev_id_in, n = 0, cnt = 0;
-    float acc = 0.f;
-    for (int t = 0; t < T; ++t) {
-        const int i = id[t];
-        if (i != blank) { acc += mp[t]; ++cnt; }   // float32 running sum, in frame order
-        if (i != prev && i != blank) tk[n++] = i;
-        prev = i;
+    __shared__ int s_id[256];
+    __shared__ float s_mp[256];
+    __shared__ int s_wcnt[8];
+    __shared__ int s_nb[8];
+    int n = 0, cnt = 0;            // running totals (meaningful in every thread)
+    float acc = 0.f;               // thread 0 only
+    for (int t0 = 0; t0 < T; t0 += 256) {
+        const int t = t0 + tid;
+        const bool in = t < T;
+        const int i = in ? id[t] : blank;
+        const int pv = !in ? blank : (t == 0 ? prev_id_in : id[t - 1]);
+        s_id[tid] = i;
+        s_mp[tid] = in ? mp[t] : 0.f;
+        const bool keep = in && i != blank && i != pv;
+        const bool nb = in && i != blank;
+        const unsigned km = __ballot_sync(0xffffffffu, keep), nm = __ballot_sync(0xffffffffu, nb);
+        if (lane == 0) { s_wcnt[warp] = __popc(km); s_nb[warp] = __popc(nm); }
+        __syncthreads();
+        int off = n, tile_keep = 0, tile_nb = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) off += s_wcnt[w];
+            tile_keep += s_wcnt[w];
+            tile_nb += s_nb[w];
+        }
+        if (keep) tk[off + __popc(km & ((1u << lane) - 1u))] = i;
+        if (tid == 0) {
+            const int m = min(256, T - t0);
+            for (int j = 0; j < m; ++j)
+                if (s_id[j] != blank) acc += s_mp[j];          // float32 running sum, in frame order
+        }
+        n += tile_keep;
+        cnt += tile_nb;
+        __syncthreads();
     }
-    ntok[b] = n;
-    psum[b] = acc;
-    pcount[b] = cnt;
+    if (tid == 0) { ntok[b] = n; psum[b] = acc; pcount[b] = cnt; }
 }
 
 }  // namespace masr
@@ -102,7 +130,7 @@ extern "C" int masr_ctc_greedy_collapse(const int* ids, const float* maxp, int64
                                         int* pcount, void* stream) {
     if (B == 0) return MASR_OK;
     MASR_REQUIRE(ids && maxp && lens && tokens && ntok && psum && pcount, "masr_ctc_greedy_collapse: null pointer");
-    ctc_greedy_collapse_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ids, maxp, bstride, lens, B, blank, -1,
-                                                                               tokens, tok_stride, ntok, psum, pcount);
+    ctc_greedy_collapse_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(ids, maxp, bstride, lens, blank, -1, tokens, tok_stride,
+                                                                    ntok, psum, pcount);
     return check_launch("ctc_greedy_collapse_kernel");
 }

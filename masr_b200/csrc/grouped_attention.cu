@@ -23,17 +23,22 @@ constexpr int GK = 8;      // key groups per shared-memory tile
 template <int DG>          // DG = group * d_k (192)
 __global__ void __launch_bounds__(GQ * 32) grouped_attention_kernel(
     const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, const float* __restrict__ P,
-    int64_t ld, int64_t bstride, const float* __restrict__ pos_u, const float* __restrict__ pos_v, float* __restrict__ O,
-    __half* __restrict__ Oh, __half* __restrict__ Ol, const int* __restrict__ lens, int H, int group, int d_model,
-    float scale) {
+    int64_t ld, int64_t bstride, int64_t ldk, int64_t k_bstride, const float* __restrict__ pos_u,
+    const float* __restrict__ pos_v, float* __restrict__ O, __half* __restrict__ Oh, __half* __restrict__ Ol,
+    const int* __restrict__ lens, const int* __restrict__ k_lens, int H, int group, int d_model, float scale) {
     constexpr int R = DG / 32;                       // values per lane
     __shared__ float sK[GK][DG], sP[GK][DG], sV[GK][DG];
     const int b = blockIdx.z, hh = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // queries: T frames at Q + b*bstride rows; keys/values: Tk frames at K/V + b*k_bstride rows of pitch ldk (the chunk
+    // path reads [cache ++ chunk] keys; both groupings start at their own first frame, attention.py:44-60)
     const int T = lens[b];
-    const int Tg = (T + group - 1) / group;          // groups incl. the zero-padded last one
+    const int Tk = k_lens[b];
+    const int Tq = (T + group - 1) / group;          // query groups incl. the zero-padded last one
+    const int Tg = (Tk + group - 1) / group;         // key groups
     const int qi = blockIdx.x * GQ + warp;
     const int64_t base = (int64_t)b * bstride * ld;
+    const int64_t kbase = (int64_t)b * k_bstride * ldk;
     // flat offset f inside a group -> (frame offset, column)
     int foff[R], fcol[R];
 #pragma unroll
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(GQ * 32) grouped_attention_kernel(
         fcol[r] = f - foff[r] * d_model;
     }
     float qu[R], qv[R], o[R];
-    const bool q_ok = qi < Tg;
+    const bool q_ok = qi < Tq;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int frame = qi * group + foff[r];
@@ -60,9 +65,9 @@ __global__ void __launch_bounds__(GQ * 32) grouped_attention_kernel(
             const int f = hh * DG + e;
             const int fo = f / d_model, fc = f - fo * d_model;
             const int frame = (k0 + kk) * group + fo;
-            const bool ok = (k0 + kk) < Tg && frame < T;
-            sK[kk][e] = ok ? __ldg(K + base + (int64_t)frame * ld + fc) : 0.f;
-            sV[kk][e] = ok ? __ldg(V + base + (int64_t)frame * ld + fc) : 0.f;
+            const bool ok = (k0 + kk) < Tg && frame < Tk;
+            sK[kk][e] = ok ? __ldg(K + kbase + (int64_t)frame * ldk + fc) : 0.f;
+            sV[kk][e] = ok ? __ldg(V + kbase + (int64_t)frame * ldk + fc) : 0.f;
             sP[kk][e] = ok ? __ldg(P + (int64_t)frame * d_model + fc) : 0.f;   // P is [T, d_model] dense, shared by the batch
         }
         __syncthreads();
@@ -130,9 +135,25 @@ extern "C" int masr_grouped_attention_f32(const float* Q, const float* K, const 
     const int max_g = (max_t + group - 1) / group;
     dim3 grid((max_g + GQ - 1) / GQ, H, B);
     grouped_attention_kernel<192><<<grid, GQ * 32, 0, (cudaStream_t)stream>>>(
-        Q, K, V, P, ld, bstride, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, lens, H, group, H * d_k,
+        Q, K, V, P, ld, bstride, ld, bstride, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, lens, lens, H, group, H * d_k,
         1.0f / sqrtf((float)(group * d_k)));
     return check_launch("grouped_attention_kernel");
+}
+
+extern "C" int masr_grouped_attention_cache_f32(const float* Q, int64_t ldq, int64_t q_bstride, const float* K, const float* V,
+                                                int64_t ldk, int64_t k_bstride, const float* P, const float* pos_u,
+                                                const float* pos_v, float* O, void* Oh, void* Ol, const int* q_lens,
+                                                const int* k_lens, int B, int H, int d_k, int group, int max_q, void* stream) {
+    if (B == 0 || max_q == 0) return MASR_OK;
+    MASR_REQUIRE(Q && K && V && P && pos_u && pos_v && (O || (Oh && Ol)) && q_lens && k_lens,
+                 "masr_grouped_attention_cache_f32: null pointer");
+    MASR_REQUIRE(group * d_k == 192 && H * d_k == 256, "masr_grouped_attention_cache_f32: this build supports group*d_k=192, d_model=256");
+    const int max_g = (max_q + group - 1) / group;
+    dim3 grid((max_g + GQ - 1) / GQ, H, B);
+    grouped_attention_kernel<192><<<grid, GQ * 32, 0, (cudaStream_t)stream>>>(
+        Q, K, V, P, ldq, q_bstride, ldk, k_bstride, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, q_lens, k_lens, H, group, H * d_k,
+        1.0f / sqrtf((float)(group * d_k)));
+    return check_launch("grouped_attention_kernel<cache>");
 }
 
 extern "C" int masr_avgpool2_time_f32(const float* x, int64_t in_bstride, float* y, int64_t out_bstride, const int* lens,

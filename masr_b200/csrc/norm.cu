@@ -70,9 +70,87 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
 }
 
+// Two LayerNorms back to back on the same row, one pass over memory: y1 = LN1(x) (fp32; may alias x), then LN2(y1) as
+// fp32 (optional) and as the fp16 (h,l) operand pair.  Same arithmetic and order as two layernorm_kernel launches (the
+// intermediate is rounded to fp32 either way), so the results are identical; it removes one launch and one 8 MB read per
+// encoder block (`norm_final` of block i followed by `norm_ff_macaron` of block i+1, encoder.py:161 + :106; after the last
+// block `norm_final` + `after_norm`, :342).
+template <int D>
+__global__ void __launch_bounds__(256) layernorm2_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g1,
+                                                         const float* __restrict__ b1, float* __restrict__ y1,
+                                                         const float* __restrict__ g2, const float* __restrict__ b2,
+                                                         float* __restrict__ y2, __half* __restrict__ yh,
+                                                         __half* __restrict__ yl, int64_t ldy, int M, float eps) {
+    static_assert(D % 128 == 0, "D must be a multiple of 128");
+    constexpr int V = D / 128;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* xr = x + (int64_t)row * ldx;
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        v[i] = ldg_f4(xr + (i * 32 + lane) * 4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const float mean = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+        const float* gp = pass ? g2 : g1;
+        const float* bp = pass ? b2 : b1;
+        s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            const float4 g = ldg_f4(gp + c), b = ldg_f4(bp + c);
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * g.x + b.x;
+            o.y = (v[i].y - mean) * rstd * g.y + b.y;
+            o.z = (v[i].z - mean) * rstd * g.z + b.z;
+            o.w = (v[i].w - mean) * rstd * g.w + b.w;
+            v[i] = o;
+            s += (o.x + o.y) + (o.z + o.w);
+            if (pass == 0) {
+                *reinterpret_cast<float4*>(y1 + (int64_t)row * ldx + c) = o;
+            } else {
+                if (y2) *reinterpret_cast<float4*>(y2 + (int64_t)row * ldy + c) = o;
+                __half hh[4], ll[4];
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hh[j] = __float2half_rn(ov[j]);
+                    ll[j] = __float2half_rn((ov[j] - __half2float(hh[j])) * 2048.0f);
+                }
+                *reinterpret_cast<uint2*>(yh + (int64_t)row * ldy + c) = *reinterpret_cast<const uint2*>(hh);
+                *reinterpret_cast<uint2*>(yl + (int64_t)row * ldy + c) = *reinterpret_cast<const uint2*>(ll);
+            }
+        }
+    }
+}
+
 }  // namespace masr
 
 using namespace masr;
+
+extern "C" int masr_layernorm2_split_f16(const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* y1,
+                                         const float* gamma2, const float* beta2, float* y2, void* yh, void* yl, int64_t ldy,
+                                         int M, int D, float eps, void* stream) {
+    if (M == 0) return MASR_OK;
+    MASR_REQUIRE(x && gamma1 && beta1 && y1 && gamma2 && beta2 && yh && yl, "masr_layernorm2_split_f16: null pointer");
+    MASR_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "masr_layernorm2_split_f16: leading dimensions must be multiples of 4");
+    MASR_REQUIRE(D == 256, "masr_layernorm2_split_f16: unsupported width D=%d (256)", D);
+    layernorm2_kernel<256><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, ldx, gamma1, beta1, y1, gamma2, beta2, y2,
+                                                                          (__half*)yh, (__half*)yl, ldy, M, eps);
+    return check_launch("layernorm2_kernel");
+}
 
 extern "C" int masr_layernorm_f32(const float* x, int64_t ldx, const float* gamma, const float* beta, float* y,
                                   int64_t ldy, int M, int D, float eps, void* stream) {

@@ -36,17 +36,6 @@ constexpr int EPI_STAGE_TOTAL = 32768;                 // epilogue store staging
 constexpr int tc_threads(int ew) { return 64 + 32 * ew; }   // TMA warp + MMA warp + EW epilogue warps
 constexpr uint32_t TMEM_COLS = 512;                    // 2 x main (ping-pong) + correction accumulator, 128 fp32 columns each (384 -> 512)
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
-// "A-resident" variant (K == 256): the whole [128 x 256] A tile pair stays in shared memory (128 KB) while the CTA walks a
-// group of N tiles, so only W streams from L2 — half the operand traffic of the plain kernel, whose K=256 GEMMs are
-// bound by L2->SM bandwidth.  W moves in 64-row half tiles (Wh + Wl = 16 KB per stage, MMA N = 64) so that
-// four stages of lookahead fit next to A.
-constexpr int AR_KB = 4;                                // K blocks of the resident A tile (K = 256)
-constexpr int AR_A_BYTES = AR_KB * 2 * TILE_BYTES;      // 128 KB
-constexpr int AR_WSTAGES = 4;
-constexpr int AR_WHALF_BYTES = 64 * TBK * 2;            // 8 KB: 64 rows x 64 halves
-constexpr int AR_WSTAGE_BYTES = 2 * AR_WHALF_BYTES;     // Wh, Wl
-static_assert(AR_A_BYTES + AR_WSTAGES * AR_WSTAGE_BYTES <= TSTAGES * STAGE_BYTES, "A-resident layout must fit the ring region");
-constexpr int RING_BARS = 4;                            // max(TSTAGES, AR_WSTAGES)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -126,22 +115,6 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, __half2& h, __ha
     const float2 hf = __half22float2(h);
     l = __floats2half2_rn((x0 - hf.x) * kLoScale, (x1 - hf.y) * kLoScale);
 }
-// Epilogue activations on the SFU (ex2.approx / rcp.approx, <= 2 ulp each): the accurate expf + IEEE divide
-// cost ~40 instructions per element and made the FFN w_1 epilogue 2.6x longer than its MMA main loop.
-// Absolute error < 2e-7 on silu/sigmoid outputs, inside the fp32-grade budget (tests/test_gpu_tc_gemm.py).
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float r;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
-__device__ __forceinline__ float fast_silu(float x) { return x * fast_sigmoid(x); }
-
 struct TcParams {
     const float* bias;
     const float* residual;
@@ -160,7 +133,6 @@ struct TcParams {
 struct TcMaps {
     CUtensorMap a[8];  // GEMM: a[0]=Ah, a[1]=Al.  CONV: a[2*plane + {0:h,1:l}], plane = (kh&1)*2 + (kw&1)
     CUtensorMap w[2];  // Wh, Wl
-    CUtensorMap w64[2];  // Wh, Wl with 64-row boxes (A-resident variant)
 };
 
 constexpr int CHUNK_KB = 4;            // K-blocks per accumulation chunk (K = 256): see "accumulation" below
@@ -395,36 +367,30 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  TMEM holds
 // main[2] (ping-pong by chunk) and corr[2] (ping-pong by tile) = 512 columns, so the MMA warp runs tile
 // i+1 while the 8 epilogue warps finish tile i.
-template <bool CONV, int EW, bool AR>
+template <bool CONV, int EW>
 __global__ void __launch_bounds__(tc_threads(EW), 1)
-tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_units, int tiles_n, int tiles_t, int g, int groups) {
-    static_assert(!(CONV && AR), "the A-resident variant is a plain GEMM");
+tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, int tiles_n, int tiles_t) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* epi_stage = smem + TSTAGES * STAGE_BYTES;                // EPI_STAGE_TOTAL / EW per warp (see staged_store)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_TOTAL);
-    uint64_t* empty_bar = full_bar + RING_BARS;
-    uint64_t* main_full = empty_bar + RING_BARS;   // [2]
+    uint64_t* empty_bar = full_bar + TSTAGES;
+    uint64_t* main_full = empty_bar + TSTAGES;     // [2]
     uint64_t* main_empty = main_full + 2;          // [2]
     uint64_t* corr_full = main_empty + 2;          // [2]
     uint64_t* corr_empty = corr_full + 2;          // [2]
-    uint64_t* a_full = corr_empty + 2;             // AR: resident A tile loaded / no longer read
-    uint64_t* a_empty = a_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.K / TBK;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]);
-        if (AR) { tma_prefetch_desc(&maps.w64[0]); tma_prefetch_desc(&maps.w64[1]); }
-        else { tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]); }
-        for (int s = 0; s < RING_BARS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]); tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
+        for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], EW);
             mbar_init(&corr_full[s], 1); mbar_init(&corr_empty[s], EW);
         }
-        mbar_init(a_full, 1); mbar_init(a_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -436,21 +402,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_units, i
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // A work unit is one output tile (plain / conv) or, A-resident, one M tile x a group of `g` consecutive N tiles.
-    // unit -> (first N tile, one past the last N tile, index of the M tile / conv row block)
-    auto unit_range = [&](int unit, int& nt0, int& nt1, int& rest) {
-        if (AR) {
-            const int grp = unit % groups;
-            rest = unit / groups;
-            nt0 = grp * g;
-            nt1 = min(nt0 + g, tiles_n);
-        } else {
-            nt0 = unit % tiles_n;
-            nt1 = nt0 + 1;
-            rest = unit / tiles_n;
-        }
-    };
-    auto decode = [&](int nt, int rest, int& n0, int& m0, int& t0, int& b) {
+    // tile -> coordinates
+    auto decode = [&](int tile, int& n0, int& m0, int& t0, int& b) {
+        const int nt = tile % tiles_n;
+        const int rest = tile / tiles_n;
         n0 = nt * TBN;
         if (CONV) { t0 = (rest % tiles_t) * CONV_TR; b = rest / tiles_t; m0 = 0; }
         else { m0 = rest * TBM; t0 = 0; b = 0; }
@@ -459,32 +414,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_units, i
     if (warp == 0) {
         if (lane == 0) {
             constexpr uint32_t a_bytes = CONV ? CONV_ROWS * TBK * 2 : TILE_BYTES;
-            uint32_t kg = 0, ug = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ug) {
-                int nt0, nt1, rest;
-                unit_range(unit, nt0, nt1, rest);
-                if (AR) {
-                    // the resident A tile: 4 K-blocks x (Ah, Al), one barrier
-                    mbar_wait(a_empty, (ug & 1) ^ 1);                  // MMAs of the previous unit have retired
-                    mbar_expect_tx(a_full, AR_A_BYTES);
-                    for (int kb = 0; kb < AR_KB; ++kb) {
-                        tma_load_2d(&maps.a[0], a_full, smem + kb * 2 * TILE_BYTES, kb * TBK, rest * TBM);
-                        tma_load_2d(&maps.a[1], a_full, smem + kb * 2 * TILE_BYTES + TILE_BYTES, kb * TBK, rest * TBM);
-                    }
-                    for (int nt = nt0; nt < nt1; ++nt)
-                        for (int kb = 0; kb < AR_KB; ++kb)
-                            for (int half = 0; half < 2; ++half, ++kg) {
-                                const uint32_t s = kg % AR_WSTAGES;
-                                mbar_wait(&empty_bar[s], ((kg / AR_WSTAGES) & 1) ^ 1);
-                                uint8_t* st = smem + AR_A_BYTES + s * AR_WSTAGE_BYTES;
-                                mbar_expect_tx(&full_bar[s], AR_WSTAGE_BYTES);
-                                tma_load_2d(&maps.w64[0], &full_bar[s], st, kb * TBK, nt * TBN + half * 64);
-                                tma_load_2d(&maps.w64[1], &full_bar[s], st + AR_WHALF_BYTES, kb * TBK, nt * TBN + half * 64);
-                            }
-                    continue;
-                }
+            uint32_t kg = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int n0, m0, t0, b;
-                decode(nt0, rest, n0, m0, t0, b);
+                decode(tile, n0, m0, t0, b);
                 for (int kb = 0; kb < nkb; ++kb, ++kg) {
                     const uint32_t s = kg % TSTAGES;
                     mbar_wait(&empty_bar[s], ((kg / TSTAGES) & 1) ^ 1);
@@ -509,46 +442,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_units, i
         if (lane == 0) {
             // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 @17, M>>4 @24
             constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-            constexpr uint32_t idesc64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-            uint32_t kg = 0, cg = 0, tl = 0, ug = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ug) {
-                int nt0, nt1, rest;
-                unit_range(unit, nt0, nt1, rest);
-                if (AR) {
-                    mbar_wait(a_full, ug & 1);
-                    tc_fence_after();
-                    const uint32_t sA = smem_u32(smem);
-                    for (int nt = nt0; nt < nt1; ++nt, ++tl, ++cg) {
-                        mbar_wait(&corr_empty[tl & 1], ((tl >> 1) & 1) ^ 1);
-                        mbar_wait(&main_empty[cg & 1], ((cg >> 1) & 1) ^ 1);
-                        tc_fence_after();
-                        for (int kb = 0; kb < AR_KB; ++kb) {
-                            const uint64_t dAh = umma_desc_k_sw128(sA + kb * 2 * TILE_BYTES);
-                            const uint64_t dAl = umma_desc_k_sw128(sA + kb * 2 * TILE_BYTES + TILE_BYTES);
-                            for (int half = 0; half < 2; ++half, ++kg) {
-                                const uint32_t s = kg % AR_WSTAGES;
-                                const uint32_t d_main = tmem_base + (cg & 1) * TBN + half * 64;
-                                const uint32_t d_corr = tmem_base + 2 * TBN + (tl & 1) * TBN + half * 64;
-                                mbar_wait(&full_bar[s], (kg / AR_WSTAGES) & 1);
-                                tc_fence_after();
-                                const uint32_t sw = sA + AR_A_BYTES + s * AR_WSTAGE_BYTES;
-                                const uint64_t dWh = umma_desc_k_sw128(sw), dWl = umma_desc_k_sw128(sw + AR_WHALF_BYTES);
-#pragma unroll
-                                for (int ks = 0; ks < TBK / 16; ++ks) {
-                                    const uint64_t adv = (uint64_t)(ks * 2);
-                                    umma_f16(d_main, dAh + adv, dWh + adv, idesc64, (kb | ks) ? 1u : 0u);
-                                    umma_f16(d_corr, dAh + adv, dWl + adv, idesc64, (kb | ks) ? 1u : 0u);
-                                    umma_f16(d_corr, dAl + adv, dWh + adv, idesc64, 1u);
-                                }
-                                umma_commit(&empty_bar[s]);
-                            }
-                        }
-                        umma_commit(&main_full[cg & 1]);
-                        umma_commit(&corr_full[tl & 1]);
-                    }
-                    umma_commit(a_empty);                              // every MMA that reads this A tile has retired
-                    continue;
-                }
+            uint32_t kg = 0, cg = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
                 mbar_wait(&corr_empty[tl & 1], ((tl >> 1) & 1) ^ 1);    // epilogue has read corr of tile tl-2
                 tc_fence_after();
                 const uint32_t d_corr = tmem_base + 2 * TBN + (tl & 1) * TBN;
@@ -577,7 +472,6 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_units, i
                     if (last) { umma_commit(&main_full[cg & 1]); ++cg; }
                 }
                 umma_commit(&corr_full[tl & 1]);                       // whole tile (incl. corrections) complete
-                ++tl;
             }
         }
     } else {
@@ -592,12 +486,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_units, i
         ctx.sb = smem_u32(epi_stage) + (warp - 2) * (EPI_STAGE_TOTAL / EW);
         ctx.lane = lane;
         uint32_t cg = 0, tl = 0;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-          int nt0, nt1, rest;
-          unit_range(unit, nt0, nt1, rest);
-          for (int nt = nt0; nt < nt1; ++nt, ++tl) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             int n0, m0, t0, b;
-            decode(nt, rest, n0, m0, t0, b);
+            decode(tile, n0, m0, t0, b);
             const int nw = n0 + cgrp * CW;                             // first column of this warp
             // bias of the warp's columns: lane l keeps columns l (and 32+l), broadcast by shuffle below;
             // fetched before the accumulator wait so its latency is hidden
@@ -686,7 +577,6 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_units, i
                 for (int j = 0; j < 32; ++j) v[j] = acc[cc * 32 + j] + __shfl_sync(0xffffffffu, bsrc, j);
                 store_chunk<BIG>(p, ctx, v, n);
             }
-          }
         }
     }
     tc_fence_before();
@@ -735,12 +625,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [rows, K] fp16 row-major (ld elements), box = 64 (K) x 128 (rows), 128-byte swizzle, zero OOB fill
-static int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows = TBM) {
+static int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point unavailable"); return MASR_ERR_INTERNAL; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -770,24 +660,9 @@ static int make_map_plane(CUtensorMap* map, const void* ptr, int B, int TH, int 
 //   bit 0  staged (row-contiguous) epilogue stores      ffn_w1 58.5 -> 42.1 us, qkv 35.5 -> 23.5, ctc head 91 -> 63
 //   bit 1  stage the residual READ as well              did not pay (w_2 31 -> 35 us); off
 //   bit 2  16 epilogue warps x 32 columns instead of 8 x 64   ffn_w1 43.1 -> 35.0 us, step 4.88 -> 4.59 ms
-//   bit 3  A-resident variant for K == 256, N >= 512 (the A tile pair stays in shared memory across a group of N tiles)
 static int tc_flags() {
     const char* e = getenv("MASR_TC_FLAGS");
     return e ? atoi(e) : 5;
-}
-
-// A-resident grouping: N tiles per work unit minimising  waves x (g + cost of the A load in tile units)
-static int ar_group_size(int tiles_m, int tiles_n, int sms) {
-    int best_g = 1;
-    double best = 1e30;
-    for (int g = 1; g <= tiles_n; ++g) {
-        const int groups = (tiles_n + g - 1) / g;
-        const long units = (long)tiles_m * groups;
-        const long waves = (units + sms - 1) / sms;
-        const double cost = (double)waves * (g + 0.5);
-        if (cost < best - 1e-9) { best = cost; best_g = g; }
-    }
-    return best_g;
 }
 
 static int num_sms() {
@@ -808,12 +683,10 @@ static int ensure_tc_attrs() {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!g_tc_attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
         if (e != cudaSuccess) { set_last_error("tc_gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         g_tc_attr_set[dev] = true;
     }
@@ -849,8 +722,8 @@ extern "C" int masr_conv2_tc_f16x2(const void* c1h, const void* c1l, const void*
     const int tiles_n = (C + TBN - 1) / TBN, tiles_t = (T2 + CONV_TR - 1) / CONV_TR;
     const int num_tiles = tiles_n * tiles_t * B;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    if (p.flags & 4) tc_gemm_kernel<true, 16, false><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t, 1, tiles_n);
-    else tc_gemm_kernel<true, 8, false><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t, 1, tiles_n);
+    if (p.flags & 4) tc_gemm_kernel<true, 16><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t);
+    else tc_gemm_kernel<true, 8><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t);
     return check_launch("tc_gemm_kernel<conv>");
 }
 
@@ -888,20 +761,8 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     TcParams p{bias, residual, C, (__half*)Ch, (__half*)Cl, ldr, ldc, M, N, K, epilogue, alpha, 0, tc_flags()};
     const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = tiles_n * tiles_m;
-    if ((p.flags & 8) && K == AR_KB * TBK && tiles_n >= 4) {
-        // A-resident: unit = M tile x group of g N tiles
-        if ((rc = make_map_2d(&maps.w64[0], Wh, N, K, K, 64))) return rc;
-        if ((rc = make_map_2d(&maps.w64[1], Wl, N, K, K, 64))) return rc;
-        const int g = ar_group_size(tiles_m, tiles_n, num_sms());
-        const int groups = (tiles_n + g - 1) / g;
-        const int num_units = tiles_m * groups;
-        const int grid = num_units < num_sms() ? num_units : num_sms();
-        if (p.flags & 4) tc_gemm_kernel<false, 16, true><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_units, tiles_n, 1, g, groups);
-        else tc_gemm_kernel<false, 8, true><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_units, tiles_n, 1, g, groups);
-        return check_launch("tc_gemm_kernel<AR>");
-    }
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    if (p.flags & 4) tc_gemm_kernel<false, 16, false><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1, 1, tiles_n);
-    else tc_gemm_kernel<false, 8, false><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1, 1, tiles_n);
+    if (p.flags & 4) tc_gemm_kernel<false, 16><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1);
+    else tc_gemm_kernel<false, 8><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1);
     return check_launch("tc_gemm_kernel");
 }

@@ -376,8 +376,10 @@ class ConformerEngine:
         self._tc(c2p, self.f2 * d, tw["embed"], w.embed_b, M, d, self.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5, C=x, ldc=d,
                  tag="embed_linear")
         lpad = (w.kernel - 1) if self.causal else (w.kernel - 1) // 2
+        nl = len(w.layers)
         for i, L in enumerate(w.layers):
-            self._ln_split(x, L.ln_ffm, t0p, M)
+            if i == 0:                                # later blocks: fused with the previous block's norm_final (below)
+                self._ln_split(x, L.ln_ffm, t0p, M)
             self._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
             self._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
             self._ln_split(x, L.ln_mha, t0p, M)
@@ -393,9 +395,11 @@ class ConformerEngine:
             self._ln_split(x, L.ln_ff, t0p, M)
             self._tc(t0p, d, tw[i, "ff1"], L.ff[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
             self._tc(hidp, w.ffn, tw[i, "ff2"], L.ff[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
-            self._ln(x, L.ln_final, x, M)
-        self._ln(x, w.after_norm, ws["t0"], M)            # fp32 encoder output (returned / tests)
-        self._ln_split(x, w.after_norm, t0p, M)           # and the pair the CTC head consumes
+            # x = norm_final(x), then in the same pass the next consumer's LayerNorm: the next block's norm_ff_macaron
+            # (pair only) or, after the last block, after_norm (fp32 encoder output + the pair the CTC head consumes)
+            nxt = w.layers[i + 1].ln_ffm if i + 1 < nl else w.after_norm
+            self._k("layernorm", "masr_layernorm2_split_f16", _p(x), d, _p(L.ln_final[0]), _p(L.ln_final[1]), _p(x), _p(nxt[0]),
+                    _p(nxt[1]), None if i + 1 < nl else _p(ws["t0"]), _p(t0p[0]), _p(t0p[1]), d, M, d, 1e-5)
         return ws["t0"][:M], tl, T, ws
 
     # ---- CTC head ----------------------------------------------------------------------------
@@ -481,10 +485,12 @@ class ConformerEngine:
 
     # ---- CUDA-graph replay of the device step (launch-bound otherwise: ~190 launches per step) ------------
     GRAPH_FRAME_QUANTUM = 32      # Fmax is rounded up so ragged batches share graphs; padding never changes results
-    STAGE_THREADS = 8             # host threads packing the pinned staging buffer (csrc/stage.cu)
+    STAGE_THREADS = 4             # host threads packing the pinned staging buffer (csrc/stage.cu)
 
-    def _graph_for(self, B: int, Fpad: int, use_db: bool, target_db: float):
-        key = (B, Fpad, use_db, float(target_db))
+    def _graph_for(self, B: int, Fpad: int, use_db: bool, target_db: float, slot: int = 0):
+        """CUDA graph of the device step for one batch shape.  ``slot`` selects one of the (double-buffered) static input
+        sets: the pipelined entry point stages batch k+1 into the other slot's buffers while batch k is computing."""
+        key = (B, Fpad, use_db, float(target_db), slot)
         g = self._graphs.get(key)
         if g is not None:
             return g
@@ -527,6 +533,92 @@ class ConformerEngine:
             self._graphs.pop(next(iter(self._graphs)))
         self._graphs[key] = g
         return g
+
+    # ---- pipelined batches: host staging + H2D of batch k+1 overlap the device step of batch k ---------------------
+    def transcribe_pipelined(self, batches, use_db_normalization: bool = True, target_db: float = -20.0):
+        """Generator over ``batches`` (an iterable of lists of float32 waveforms) yielding one ``GreedyResult`` per batch,
+        in order, each identical to ``transcribe(batch)``.  Two static input sets + two pinned staging buffers: while the
+        CUDA graph of batch k runs on the compute stream, batch k+1 is packed into pinned memory by the native stager and
+        copied H2D on a separate copy stream; the packed outputs of batch k come back in one D2H copy.  Results lag the
+        input by one batch."""
+        dev = self.device
+        comp = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._pipe = [{"pinned": None, "out": None, "staged": torch.cuda.Event(), "done": torch.cuda.Event()} for _ in range(2)]
+        copy = self._copy_stream
+        prev = None
+        k = 0
+
+        def finish(item):
+            slot, B, T, tl, ws_tok_T, has = item
+            if not has:
+                return GreedyResult([[] for _ in range(B)], [0.0] * B, None, np.zeros(B, np.int32), np.zeros(B, np.int32))
+            P = self._pipe[slot]
+            P["done"].synchronize()
+            on = P["out"][:B * ws_tok_T + 4 * B].numpy()
+            tok = on[:B * ws_tok_T].reshape(B, ws_tok_T)
+            ntok = on[B * ws_tok_T:B * ws_tok_T + B]
+            pcnt = on[B * ws_tok_T + B:B * ws_tok_T + 2 * B]
+            st_h = on[B * ws_tok_T + 2 * B:B * ws_tok_T + 3 * B].copy()
+            psum = on[B * ws_tok_T + 3 * B:B * ws_tok_T + 4 * B].view(np.float32)
+            self.d2h_bytes += on.nbytes
+            tokens = [tok[b, :ntok[b]].tolist() for b in range(B)]
+            scores = [greedy_score(psum[b], pcnt[b]) for b in range(B)]
+            return GreedyResult(tokens, scores, None, np.asarray(tl, np.int32), st_h)
+
+        for waves in batches:
+            slot = k & 1
+            k += 1
+            B = len(waves)
+            lengths = [int(w.shape[0]) for w in waves]
+            frames = [num_frames(n) for n in lengths]
+            q = self.GRAPH_FRAME_QUANTUM
+            Fpad = max(q, (max(frames) + q - 1) // q * q) if B else q
+            tl1 = [subsampled_len(f) for f in frames]
+            tl = [self.final_len(t) for t in tl1]
+            if B == 0 or max(tl) == 0:
+                item = (slot, B, 0, tl, 0, False)
+            else:
+                g = self._graph_for(B, Fpad, use_db_normalization, target_db, slot)      # (captures on first use)
+                P = self._pipe[slot]
+                offs = np.zeros(B + 1, np.int64)
+                np.cumsum(lengths, out=offs[1:])
+                total = int(offs[-1])
+                need = total + 4 * (B + 2) + 8
+                if P["pinned"] is None or P["pinned"].numel() < need:
+                    P["pinned"] = torch.empty((int(1.25 * need) + 1024) // 2 * 2, dtype=torch.float32, pin_memory=True)
+                pin = P["pinned"]
+                waves = [w if (w.dtype == np.float32 and w.flags.c_contiguous) else np.ascontiguousarray(w, np.float32) for w in waves]
+                ptrs = (_lib.C.c_void_p * B)(*[w.ctypes.data for w in waves])
+                lens_c = (_lib.C.c_int64 * B)(*lengths)
+                # the slot's previous batch (k-2) was consumed before its result was yielded: its buffers are free
+                call("masr_stage_waves_f32", ptrs, lens_c, B, pin.data_ptr(), g["wave"].data_ptr(), self.STAGE_THREADS,
+                     copy.cuda_stream)
+                t0 = (total + 1) // 2 * 2
+                po = pin[t0:t0 + 2 * (B + 1)].view(torch.int64)
+                po.numpy()[:] = offs
+                pt = pin[t0 + 2 * (B + 1):t0 + 2 * (B + 1) + B].view(torch.int32)
+                pt.numpy()[:] = tl1
+                with torch.cuda.stream(copy):
+                    g["offs"].copy_(po, non_blocking=True)
+                    g["tlens"].copy_(pt, non_blocking=True)
+                    P["staged"].record(copy)
+                self.h2d_bytes += 4 * total + 8 * (B + 1) + 4 * B
+                comp.wait_event(P["staged"])
+                g["graph"].replay()
+                self.launches += g["launches"]
+                pack = g["ws"]["out_pack"]
+                if P["out"] is None or P["out"].numel() < pack.numel():
+                    P["out"] = torch.empty(max(4096, 2 * pack.numel()), dtype=torch.int32, pin_memory=True)
+                P["out"][:pack.numel()].copy_(pack, non_blocking=True)
+                P["done"].record(comp)
+                item = (slot, B, g["T"], tl, g["ws"]["tokens"].shape[1], True)
+            if prev is not None:
+                yield finish(prev)
+            prev = item
+        if prev is not None:
+            yield finish(prev)
 
     def prepare_resident(self, waves: Sequence[np.ndarray], use_db: bool = True, target_db: float = -20.0):
         """Stage a batch into the static device buffers of its CUDA graph and return a zero-argument callable
@@ -802,7 +894,7 @@ class EfficientConformerEngine(ConformerEngine):
     """EfficientConformer (configs/efficient_conformer.yml; masr/model_utils/efficient_conformer/encoder.py:25-265):
     Conformer blocks with grouped attention in blocks 0-3 (group 3), a strided conv module in block 3
     (T -> ceil(T/2), AvgPool residual) and depthwise kernel 7 from block 4 on; the output is at 80 ms frames.
-    Whole-utterance (batched) path only; tensor-core GEMMs."""
+    Whole-utterance (batched) path here; chunk decoding in stream_pool.EfficientConformerStreamPool.  Tensor-core GEMMs."""
 
     STRIDE_LAYER = 3
     GROUP = 3
@@ -823,11 +915,17 @@ class EfficientConformerEngine(ConformerEngine):
     def final_len(self, t: int) -> int:
         return (t + 1) // 2
 
-    def new_stream(self):
-        raise NotImplementedError("chunk (streaming) decoding is implemented for the Conformer only so far")
+    def new_stream(self, max_frames: int = 3000):
+        """Streaming state of one utterance (att/cnn caches + offset): a one-slot stream pool."""
+        from .stream_pool import EfficientConformerStreamPool, PoolStream
+        return PoolStream(EfficientConformerStreamPool(self, 1, max_frames))
 
-    def encode_chunk(self, *a, **k):
-        raise NotImplementedError("chunk (streaming) decoding is implemented for the Conformer only so far")
+    def encode_chunk(self, feats_chunk, st, required_cache_size: int = -1, want_probs: bool = False):
+        """``EfficientConformerModel.get_encoder_out_chunk`` for one stream (encoder.py:267-392): feats_chunk [n<=67, 80] on
+        device -> (ids, max-prob) device tensors, one per 80 ms output frame."""
+        if want_probs:
+            raise NotImplementedError("posteriors of the chunk path are not exposed for this model")
+        return st.encode_chunk(feats_chunk, required_cache_size)
 
     def _encode_tc(self, feats, ws, tl, tlens, B, Fmax, F1, T, M):
         w, d, tw = self.w, self.d, self._tcw

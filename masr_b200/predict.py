@@ -112,7 +112,7 @@ class MASRPredictor:
             raise Exception(f"masr_b200: model '{self.configs.use_model}' is not implemented yet "
                             f"(available: {sorted(engines)})")
         self.predictor = engines[self.configs.use_model](model_path, streaming=bool(self.configs.streaming))
-        self._can_stream = self.configs.use_model in ('conformer', 'deepspeech2', 'squeezeformer')
+        self._can_stream = self.configs.use_model in ('conformer', 'deepspeech2', 'squeezeformer', 'efficient_conformer')
         if self.predictor.V != self._text_featurizer.vocab_size:
             raise Exception(f"vocabulary has {self._text_featurizer.vocab_size} entries but the model's CTC head has "
                             f"{self.predictor.V}")
@@ -170,6 +170,29 @@ class MASRPredictor:
         self._raise_status(res.status)
         vocab = self._text_featurizer.vocab_list
         return [{'text': ids_to_text(t, vocab), 'score': s} for t, s in zip(res.tokens, res.scores)]
+
+    def predict_batches(self, batches, sample_rate=16000):
+        """Additive: a stream of batches (iterable of lists of utterances) -> one list of ``{'text','score'}`` per batch, in
+        order; element i of batch k equals ``predict(batches[k][i])``.  Host staging and the H2D copy of batch k+1 overlap
+        the GPU pass of batch k (``ConformerEngine.transcribe_pipelined``), so the results lag the input by one batch.
+        Greedy decoding only."""
+        if self._beam_conf is not None:
+            for b in batches:
+                yield self.predict_batch(b, sample_rate)
+            return
+        vocab = self._text_featurizer.vocab_list
+
+        def loaded():
+            for audio_list in batches:
+                waves = []
+                for a in audio_list:
+                    s, sr = load_audio(a, sample_rate)
+                    self._check_rate(sr)
+                    waves.append(s)
+                yield waves
+        for res in self.predictor.transcribe_pipelined(loaded(), self._use_db, self._target_db):
+            self._raise_status(res.status)
+            yield [{'text': ids_to_text(t, vocab), 'score': s} for t, s in zip(res.tokens, res.scores)]
 
     @staticmethod
     def _raise_status(status):

@@ -297,6 +297,169 @@ class SqueezeformerStreamPool:
         return b["ids"].view(S, C), b["maxp"].view(S, C), tout
 
 
+class EfficientConformerStreamPool:
+    """Batched chunk decoding for the streaming EfficientConformer (``EfficientConformerEncoder.forward_chunk``,
+    masr/model_utils/efficient_conformer/encoder.py:267-392, ``required_cache_size < 0``).
+
+    Blocks 0-3 run at 40 ms frames with grouped attention over a float32 K|V cache (keys regrouped from key 0, queries from
+    the first chunk frame, attention.py:44-60); block 3's conv module strides by 2 (16 -> 8 frames, AvgPool residual);
+    blocks 4-11 run at 80 ms frames (depthwise kernel 7) over fp16-pair K|V caches kept at that rate — the reference stores
+    them ``repeat_interleave``d and reads them back with ``[::2]`` (:344,372), a round trip.  The caller's offset counts
+    output frames and is doubled inside (:306).  One chunk yields 8 output frames.  A short final chunk is supported once
+    per stream (reset afterwards)."""
+
+    def __init__(self, eng, n_slots: int, max_frames: int = 3000):
+        if not eng.causal:
+            raise Exception("chunk decoding needs a streaming (causal) model")
+        self.eng, self.S = eng, n_slots
+        self.cap = (max_frames + 15) // 16 * 16
+        self.cap2 = self.cap // 2
+        dev, d, w = eng.device, eng.d, eng.w
+        f16, f32 = torch.float16, torch.float32
+        S, C = n_slots, CHUNK_OUT
+        C2 = C // 2
+        self.SL = eng.STRIDE_LAYER
+        F1 = (CHUNK_FRAMES - 1) // 2
+        TH = (F1 + 1) // 2
+        M = S * C
+        self.kv32 = {i: torch.zeros(S * self.cap, 2 * d, device=dev, dtype=f32) for i, L in enumerate(w.layers) if L.grouped}
+        self.kv = {i: (torch.zeros(S * (self.cap if i <= self.SL else self.cap2), 2 * d, device=dev, dtype=f16),
+                       torch.zeros(S * (self.cap if i <= self.SL else self.cap2), 2 * d, device=dev, dtype=f16))
+                   for i, L in enumerate(w.layers) if not L.grouped}
+        self.xcat = [(torch.zeros(S, (L.kernel - 1) + (C if i <= self.SL else C2), d, device=dev, dtype=f16),
+                      torch.zeros(S, (L.kernel - 1) + (C if i <= self.SL else C2), d, device=dev, dtype=f16))
+                     for i, L in enumerate(w.layers)]
+        self.lens_host = [0] * S
+        LCmax = max(x[0].shape[1] for x in self.xcat)
+        self.b = {
+            "c1p": (torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16), torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16)),
+            "c2p": (torch.empty(M * eng.f2, d, device=dev, dtype=f16), torch.empty(M * eng.f2, d, device=dev, dtype=f16)),
+            "x": torch.zeros(M, d, device=dev, dtype=f32), "t0": torch.zeros(M, d, device=dev, dtype=f32),
+            "t0p": (torch.zeros(M, d, device=dev, dtype=f16), torch.zeros(M, d, device=dev, dtype=f16)),
+            "t1p": (torch.zeros(M, d, device=dev, dtype=f16), torch.zeros(M, d, device=dev, dtype=f16)),
+            "hidp": (torch.empty(M, w.ffn, device=dev, dtype=f16), torch.empty(M, w.ffn, device=dev, dtype=f16)),
+            "qb": torch.zeros(M, d, device=dev, dtype=f32), "kvn": torch.zeros(M, 2 * d, device=dev, dtype=f32),
+            "qkv": torch.zeros(M, 3 * d, device=dev, dtype=f32),
+            "qkvp": (torch.zeros(M, 3 * d, device=dev, dtype=f16), torch.zeros(M, 3 * d, device=dev, dtype=f16)),
+            "g": torch.empty(S * LCmax, d, device=dev, dtype=f32),
+            "logits": torch.empty(S * C2, eng.Vpad, device=dev, dtype=f32),
+            "ids": torch.empty(S * C2, device=dev, dtype=torch.int32), "maxp": torch.empty(S * C2, device=dev, dtype=f32),
+            "qlen": torch.zeros(S, device=dev, dtype=torch.int32), "klen": torch.zeros(S, device=dev, dtype=torch.int32),
+            "qlen2": torch.zeros(S, device=dev, dtype=torch.int32), "klen2": torch.zeros(S, device=dev, dtype=torch.int32),
+            "clen": torch.full((S,), LCmax, device=dev, dtype=torch.int32),
+        }
+
+    def reset(self, slot: int):
+        self.lens_host[slot] = 0
+        for xh, xl in self.xcat:
+            xh[slot].zero_()
+            xl[slot].zero_()
+
+    def step(self, feats: torch.Tensor, nframes: Sequence[int]):
+        """feats [S, 67, 80] raw log-mel (device), nframes[s] = valid feature frames of slot s (0 = idle).
+        -> (ids [S,8] int32, maxp [S,8], tout) with tout[s] = ceil((((n-1)//2-1)//2) / 2) valid output frames."""
+        eng, S, C = self.eng, self.S, CHUNK_OUT
+        C2 = C // 2
+        w, d, tw, b = eng.w, eng.d, eng._tcw, self.b
+        dev = eng.device
+        tout = [subsampled_len(int(n)) for n in nframes]
+        tout2 = [(t + 1) // 2 for t in tout]
+        for s in range(S):
+            if tout[s] and self.lens_host[s] % C:
+                raise AssertionError(f"stream slot {s}: a short (final) chunk was already decoded; reset the stream first")
+            if self.lens_host[s] + tout[s] > self.cap or self.lens_host[s] + tout[s] >= w.max_len:
+                raise AssertionError(f"stream slot {s}: {self.lens_host[s] + tout[s]} cached frames exceed the pool capacity")
+        b["qlen"].copy_(torch.tensor(tout, dtype=torch.int32))
+        b["klen"].copy_(torch.tensor([self.lens_host[s] + tout[s] for s in range(S)], dtype=torch.int32))
+        b["qlen2"].copy_(torch.tensor(tout2, dtype=torch.int32))
+        b["klen2"].copy_(torch.tensor([self.lens_host[s] // 2 + tout2[s] for s in range(S)], dtype=torch.int32))
+
+        def scatter(cap, base, cnt, stride):
+            rows = torch.tensor([s * cap + base[s] + t for s in range(S) for t in range(cnt[s])], dtype=torch.int64, device=dev)
+            src = torch.tensor([s * stride + t for s in range(S) for t in range(cnt[s])], dtype=torch.int64, device=dev)
+            return rows, src
+        sc_full = scatter(self.cap, self.lens_host, tout, C)
+        sc_half = scatter(self.cap2, [n // 2 for n in self.lens_host], tout2, C2)
+        M, M2 = S * C, S * C2
+        F1 = (CHUNK_FRAMES - 1) // 2
+        x, t0, t0p, t1p, hidp, qkv, qkvp, g, qb, kvn = (b["x"], b["t0"], b["t0p"], b["t1p"], b["hidp"], b["qkv"], b["qkvp"],
+                                                         b["g"], b["qb"], b["kvn"])
+        eng._k("conv1", "masr_conv1_cmvn_relu_planes_f16", _p(feats), _p(w.cmvn_mean), _p(w.cmvn_istd), _p(w.conv1_w), _p(w.conv1_b),
+               _p(b["c1p"][0]), _p(b["c1p"][1]), S, CHUNK_FRAMES, w.idim, F1, eng.w1_cols, d)
+        eng._k("conv2", "masr_conv2_tc_f16x2", _p(b["c1p"][0]), _p(b["c1p"][1]), _p(tw["conv2"][0]), _p(tw["conv2"][1]), _p(w.conv2_b),
+               None, _p(b["c2p"][0]), _p(b["c2p"][1]), S, F1, C, d)
+        eng._tc(b["c2p"], eng.f2 * d, tw["embed"], w.embed_b, M, d, eng.f2 * d, EPI_BIAS_SCALE, float(d) ** 0.5, C=x, ldc=d)
+        for i, L in enumerate(w.layers):
+            half = i > self.SL
+            Mi, Ci = (M2, C2) if half else (M, C)
+            qlen, klen = (b["qlen2"], b["klen2"]) if half else (b["qlen"], b["klen"])
+            rows, src = sc_half if half else sc_full
+            cap = self.cap2 if half else self.cap
+            lorder = L.kernel - 1
+            LCi = lorder + Ci
+            eng._ln_split(x, L.ln_ffm, t0p, Mi)
+            eng._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], Mi, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
+            eng._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], Mi, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d)
+            eng._ln_split(x, L.ln_mha, t0p, Mi)
+            if L.grouped:
+                wh, wl = tw[i, "qkv"]
+                eng._tc(t0p, d, (wh[:d], wl[:d]), L.bqkv[:d], Mi, d, d, C=qb, ldc=d)
+                eng._tc(t0p, d, (wh[d:], wl[d:]), L.bqkv[d:], Mi, 2 * d, d, C=kvn, ldc=2 * d)
+                kc = self.kv32[i]
+                if rows.numel():
+                    kc.index_copy_(0, rows, kvn.index_select(0, src))
+                eng._k("attention", "masr_grouped_attention_cache_f32", _p(qb), d, Ci, kc.data_ptr(), kc.data_ptr() + 4 * d, 2 * d, cap,
+                       _p(L.ptab), _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), _p(qlen), _p(klen), S, eng.h, eng.dk,
+                       eng.GROUP, Ci)
+            else:
+                eng._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, Cp=qkvp, ldc=3 * d)
+                kvh, kvl = self.kv[i]
+                if rows.numel():
+                    kvh.index_copy_(0, rows, qkvp[0][:Mi].index_select(0, src)[:, d:])
+                    kvl.index_copy_(0, rows, qkvp[1][:Mi].index_select(0, src)[:, d:])
+                ph, pl, _ = eng._ptab_pair(L)
+                eng._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, Ci, kvh.data_ptr(), kvl.data_ptr(), kvh.data_ptr() + 2 * d,
+                       kvl.data_ptr() + 2 * d, 2 * d, cap, _p(ph), _p(pl), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), d, Ci,
+                       _p(qlen), _p(klen), S, eng.h, eng.dk, Ci)
+            eng._tc(t1p, d, tw[i, "wo"], L.bo, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d)
+            # conv module over [cache ++ chunk] per slot (convolution.py:93-111)
+            eng._ln_split(x, L.ln_conv, t0p, Mi)
+            xh, xl = self.xcat[i]
+            xh[:, lorder:].copy_(t0p[0][:Mi].view(S, Ci, d))
+            xl[:, lorder:].copy_(t0p[1][:Mi].view(S, Ci, d))
+            eng._tc((xh, xl), d, tw[i, "pw1"], L.pw1_b, S * LCi, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d)
+            cnt = tout2 if half else tout
+            if i == self.SL:
+                eng._k("dwconv_ln_silu", "masr_dwconv_ln_silu_strided_f32", _p(g), d, LCi, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]),
+                       None, None, _p(t1p[0]), _p(t1p[1]), d, C2, _p(b["clen"]), S, d, L.kernel, 0, 2, C2, 1e-5)
+                eng._k("avgpool", "masr_avgpool2_time_f32", _p(x), C, _p(t0), C2, _p(b["qlen"]), S, C2, d)
+                Mo, res = M2, t0
+            else:
+                eng._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, LCi, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]), None,
+                       None, _p(t1p[0]), _p(t1p[1]), d, Ci, _p(b["clen"]), S, d, L.kernel, 0, Ci, 1e-5)
+                Mo, res = Mi, x
+            # new left context = the last `lorder` VALID rows of [cache ++ chunk]
+            if all(t == Ci for t in cnt):
+                xh[:, :lorder].copy_(xh[:, Ci:Ci + lorder].clone())
+                xl[:, :lorder].copy_(xl[:, Ci:Ci + lorder].clone())
+            else:
+                for s in range(S):
+                    if cnt[s]:
+                        xh[s, :lorder].copy_(xh[s, cnt[s]:cnt[s] + lorder].clone())
+                        xl[s, :lorder].copy_(xl[s, cnt[s]:cnt[s] + lorder].clone())
+            eng._tc(t1p, d, tw[i, "pw2"], L.pw2_b, Mo, d, d, EPI_RESIDUAL, 1.0, res, d, C=x, ldc=d)
+            eng._ln_split(x, L.ln_ff, t0p, Mo)
+            eng._tc(t0p, d, tw[i, "ff1"], L.ff[1], Mo, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
+            eng._tc(hidp, w.ffn, tw[i, "ff2"], L.ff[3], Mo, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d)
+            eng._ln(x, L.ln_final, x, Mo)
+        eng._ln_split(x, w.after_norm, t0p, M2)
+        eng._tc(t0p, d, tw["ctc"], w.ctc_b, M2, eng.V, d, C=b["logits"], ldc=eng.Vpad)
+        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M2, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
+        for s in range(S):
+            self.lens_host[s] += tout[s]
+        return b["ids"].view(S, C2), b["maxp"].view(S, C2), tout2
+
+
 class PoolStream:
     """One stream = a one-slot pool behind the single-stream interface ``MASRPredictor.predict_stream`` uses
     (``eng.new_stream()`` / ``eng.encode_chunk(chunk, stream)``)."""
@@ -324,9 +487,12 @@ class PoolStream:
 
 def make_pool(eng, n_slots: int, max_frames: int = 3000):
     """The batched chunk-decoding pool that matches the engine's model family."""
+    from .engine import EfficientConformerEngine
     from .squeezeformer import SqueezeformerEngine
     if isinstance(eng, SqueezeformerEngine):
         return SqueezeformerStreamPool(eng, n_slots, max_frames)
+    if isinstance(eng, EfficientConformerEngine):
+        return EfficientConformerStreamPool(eng, n_slots, max_frames)
     if type(eng) is ConformerEngine:
         return ConformerStreamPool(eng, n_slots, max_frames)
     raise NotImplementedError(f"no stream pool for {type(eng).__name__}")

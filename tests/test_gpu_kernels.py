@@ -216,3 +216,51 @@ def test_stage_waves(rt, lens, threads):
     assert np.array_equal(dev[:total].cpu().numpy(), ref)
     assert np.array_equal(pinned[:total].numpy(), ref)
     assert torch.isnan(dev[total:]).all()
+
+
+def test_ctc_collapse_long_and_ragged(rt):
+    """Collapse over several 256-frame tiles: repeats across tile borders, blanks, an empty utterance, synthetic ids."""
+    from oracle import ctc as octc
+    rng = np.random.default_rng(9)
+    lens = [0, 1, 255, 256, 257, 700, 1500]
+    B, T = len(lens), max(lens)
+    ids = rng.integers(0, 4, size=(B, T)).astype(np.int32)           # few symbols -> many repeats and blanks
+    ids[5, 250:262] = 3                                               # a run across the first tile border
+    ids[6, 500:530] = 0
+    mp = rng.random((B, T)).astype(np.float32)
+    d = lambda a: torch.from_numpy(a).to(rt.dev)
+    idd, mpd, ld = d(ids), d(mp), d(np.asarray(lens, np.int32))
+    tok = torch.full((B, T), -1, dtype=torch.int32, device=rt.dev); nt = torch.empty(B, dtype=torch.int32, device=rt.dev)
+    ps = torch.empty(B, device=rt.dev); pc = torch.empty(B, dtype=torch.int32, device=rt.dev)
+    rt.call("masr_ctc_greedy_collapse", P(idd), P(mpd), T, P(ld), B, 0, P(tok), T, P(nt), P(ps), P(pc), rt.st())
+    for b, n in enumerate(lens):
+        fr = ids[b, :n]
+        assert tok[b, :nt[b].item()].cpu().tolist() == octc.collapse(fr), b
+        acc = np.float32(0)
+        for t in range(n):
+            if fr[t] != 0:
+                acc = np.float32(acc + mp[b, t])
+        assert pc[b].item() == int((fr != 0).sum())
+        assert ps[b].item() == float(acc), b
+
+
+def test_layernorm2_is_two_layernorms(rt):
+    """masr_layernorm2_split_f16 == masr_layernorm_f32 followed by masr_layernorm_split_f16, bit for bit (in place too)."""
+    g = torch.Generator().manual_seed(11)
+    M, D = 1003, 256
+    x = (torch.randn(M, D, generator=g) * 3 + 0.5).to(rt.dev)
+    g1, b1, g2, b2 = (torch.randn(D, generator=g).to(rt.dev) for _ in range(4))
+    y1 = torch.empty_like(x)
+    rt.call("masr_layernorm_f32", P(x), D, P(g1), P(b1), P(y1), D, M, D, 1e-5, rt.st())
+    y2 = torch.empty_like(x)
+    rt.call("masr_layernorm_f32", P(y1), D, P(g2), P(b2), P(y2), D, M, D, 1e-5, rt.st())
+    rh = torch.empty(M, D, dtype=torch.float16, device=rt.dev); rl = torch.empty_like(rh)
+    rt.call("masr_layernorm_split_f16", P(y1), D, P(g2), P(b2), P(rh), P(rl), D, M, D, 1e-5, rt.st())
+    xin = x.clone()
+    o2 = torch.full_like(x, float("nan"))
+    oh = torch.empty_like(rh); ol = torch.empty_like(rl)
+    rt.call("masr_layernorm2_split_f16", P(xin), D, P(g1), P(b1), P(xin), P(g2), P(b2), P(o2), P(oh), P(ol), D, M, D, 1e-5, rt.st())
+    torch.cuda.synchronize()
+    assert torch.equal(xin, y1) and torch.equal(o2, y2) and torch.equal(oh, rh) and torch.equal(ol, rl)
+    ref = F.layer_norm(F.layer_norm(x.cpu(), (D,), g1.cpu(), b1.cpu()), (D,), g2.cpu(), b2.cpu())
+    assert maxdiff(o2, ref) < 2e-5

@@ -119,6 +119,24 @@ def test_batch_is_permutation_and_batchsize_invariant(gpu_engines):
     assert again.tokens == full.tokens and again.scores == full.scores       # deterministic
 
 
+def test_pipelined_batches_equal_synchronous_calls(gpu_engines):
+    """transcribe_pipelined (double-buffered staging on a copy stream) returns, batch by batch, exactly what transcribe
+    returns; shapes change between batches, one batch is empty of frames, the same shape repeats (both slots reused)."""
+    eng = gpu_engines()
+    rng = np.random.default_rng(5)
+    batches = []
+    for k in range(7):
+        nb = [3, 5, 3, 1, 3, 3, 2][k]
+        batches.append([synth.noise_audio(300 + 10 * k + i, int(rng.integers(8000, 60000))) for i in range(nb)])
+    batches[3] = [np.zeros(100, np.float32) + 0.01]          # shorter than one frame
+    want = [eng.transcribe(b) for b in batches]
+    got = list(eng.transcribe_pipelined(iter(batches)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.tokens == w.tokens and g.scores == w.scores
+    assert list(eng.transcribe_pipelined(iter([]))) == []
+
+
 def test_simt_gemm_path_matches_oracle(gpu_engines):
     """The fp32 FMA-pipe GEMM build of the same layer program (also what the chunk path uses)."""
     from masr_b200.engine import ConformerEngine
@@ -180,6 +198,8 @@ def test_predictor_dropin_whole_utterance(predictor, predictor_golden):
     # int16 ndarray and WAV bytes of the same audio are accepted like the reference accepts them
     out = predictor.predict_batch([x.copy(), x[:20000].copy()])
     assert _same(out[0], g["whole"])
+    outs = list(predictor.predict_batches([[x.copy()], [x[:20000].copy(), x.copy()], [x.copy()]]))
+    assert _same(outs[0][0], g["whole"]) and _same(outs[1][1], g["whole"]) and _same(outs[2][0], g["whole"]) and outs[1][0] == out[1]
 
 
 def test_predictor_dropin_streaming(predictor, predictor_golden):

@@ -51,10 +51,8 @@ def test_predict_matches_oracle(tmp_path, use_model):
         pred.reset_stream()
         got = [pred.predict_stream(audio_data=pcm[s:s + 8000].tobytes(), is_end=s + 8000 >= len(pcm)) for s in range(0, len(pcm), 8000)]
         assert got[-1] is not None and isinstance(got[-1]["text"], str)
-    elif use_model == "efficient_conformer":
-        with pytest.raises(NotImplementedError):
-            pred.predict_stream(audio_data=pcm[:8000].tobytes())
-    # (the Squeezeformer's streaming path is pinned to the reference in tests/test_squeezeformer_stream.py)
+    # (the Squeezeformer / EfficientConformer streaming paths are pinned to the reference in
+    #  tests/test_squeezeformer_stream.py and tests/test_efficient_stream.py)
 
 
 def test_beam_search_decoder_config(tmp_path):

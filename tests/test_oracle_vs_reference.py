@@ -100,3 +100,40 @@ def test_squeezeformer_chunk_forward_matches():
             assert (pr - pm).abs().max().item() < 5e-6          # fp32 summation-order noise (different operand strides)
             assert att.shape == st.att_cache.shape and (att - st.att_cache).abs().max().item() < 2e-5
             assert cnn.shape == st.cnn_cache.shape and (cnn - st.cnn_cache).abs().max().item() < 2e-5
+
+
+def test_efficient_conformer_chunk_forward_matches():
+    """oracle/efficient_conformer.get_encoder_out_chunk against the live reference, chunk by chunk (probabilities and
+    both caches), including a short final chunk."""
+    ref_shims.install()
+    import tempfile
+    import yaml
+    from masr.model_utils.efficient_conformer.model import EfficientConformerModel
+    from oracle import efficient_conformer as oe
+    cfg_y = yaml.safe_load(open(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "efficient_conformer.yml"), encoding="utf-8"))
+    with tempfile.TemporaryDirectory() as tmp:
+        mi = os.path.join(tmp, "mi.json")
+        synth.write_mean_istd(mi, 0)
+        m = EfficientConformerModel(input_dim=80, vocab_size=synth.DEFAULT_VOCAB_SIZE, mean_istd_path=mi, streaming=True,
+                                    encoder_conf=cfg_y["encoder_conf"], decoder_conf=cfg_y["decoder_conf"], **cfg_y["model_conf"]).eval()
+    sdn = synth.efficient_conformer_state_dict(0)
+    m.load_state_dict(synth.to_torch(sdn), strict=False)
+    sd = synth.to_torch(sdn)
+    cfg = oe.EfficientConfig()
+    feat = torch.from_numpy(ob.featurize(make_audio("speech", 13, 16000 * 3 + 4000)))[None]
+    with torch.no_grad():
+        st = oe.ChunkState()
+        att = torch.zeros(0, 0, 0, 0)
+        cnn = torch.zeros(0, 0, 0, 0)
+        off = 0
+        nf = feat.shape[1]
+        for cur in range(0, nf - 7 + 1, 64):
+            ch = feat[:, cur:min(cur + 67, nf)]
+            pr, att, cnn = m.get_encoder_out_chunk(ch, off, -16, att, cnn)
+            off += pr.shape[1]
+            pm = oe.get_encoder_out_chunk(sd, cfg, ch, st, -16)
+            assert pr.shape == pm.shape
+            assert torch.equal(pr.argmax(-1), pm.argmax(-1))
+            assert (pr - pm).abs().max().item() < 5e-6
+            assert att.shape == st.att_cache.shape and (att - st.att_cache).abs().max().item() < 2e-5
+            assert cnn.shape == st.cnn_cache.shape and (cnn - st.cnn_cache).abs().max().item() < 2e-5

@@ -1,0 +1,57 @@
+"""Dev tool / BASELINE.json config 3: `configs/squeezeformer.yml` streaming, N live streams (default 64), every stream pushes
+0.5 s (8000-sample) int16 PCM chunks; `StreamPool.push` = the `predict_stream` semantics of the reference for every stream
+(67-frame windows, stride 64, greedy) with one batched chunk step per round.  Prints one JSON line: audio-s/s, per-push
+latency (ms), launches per push.  Also runs the Conformer with --model conformer.  Synthetic audio + weights."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from masr_b200 import synth
+from masr_b200.stream_pool import StreamPool
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--model", default="squeezeformer", choices=["squeezeformer", "conformer", "efficient_conformer"])
+ap.add_argument("--streams", type=int, default=64)
+ap.add_argument("--pushes", type=int, default=40)
+ap.add_argument("--warm", type=int, default=6)
+args = ap.parse_args()
+
+if args.model == "squeezeformer":
+    from masr_b200.squeezeformer import SqueezeformerEngine
+    eng = SqueezeformerEngine(synth.squeezeformer_state_dict(0, streaming=True), streaming=True)
+elif args.model == "efficient_conformer":
+    from masr_b200.engine import EfficientConformerEngine
+    eng = EfficientConformerEngine(synth.efficient_conformer_state_dict(0), streaming=True)
+else:
+    from masr_b200.engine import ConformerEngine
+    eng = ConformerEngine(synth.conformer_state_dict(0), streaming=True)
+S, PUSH = args.streams, 8000
+total = (args.warm + args.pushes) * PUSH
+pcm = [(np.clip(synth.noise_audio(500 + s, total), -1, 1) * 32767).astype("<i2") for s in range(S)]
+pool = StreamPool(eng, synth.vocabulary(), n_slots=S, max_frames=((total // 160) // 4 + 64))
+lat = []
+l0 = None
+for k in range(args.warm + args.pushes):
+    if k == args.warm:
+        torch.cuda.synchronize()
+        t_start = time.perf_counter()
+        l0 = eng.launches
+    t0 = time.perf_counter()
+    out = pool.push({s: pcm[s][k * PUSH:(k + 1) * PUSH].tobytes() for s in range(S)}, is_end=False)
+    torch.cuda.synchronize()
+    if k >= args.warm:
+        lat.append((time.perf_counter() - t0) * 1e3)
+wall = time.perf_counter() - t_start
+audio = S * args.pushes * PUSH / 16000.0
+lat = np.asarray(lat)
+print(json.dumps({"config": f"{args.model} streaming, {S} live streams x {args.pushes} pushes of 0.5 s, predict_stream semantics, ctc_greedy",
+                  "audio_seconds_per_second": audio / wall, "push_latency_ms": {"mean": float(lat.mean()), "p50": float(np.median(lat)),
+                                                                                "p95": float(np.percentile(lat, 95)), "max": float(lat.max())},
+                  "real_time_factor_per_stream": (wall / args.pushes) / 0.5, "kernel_launches_per_push": (eng.launches - l0) / args.pushes,
+                  "sample_text_len": len(next(v for v in out.values() if v is not None)["text"]) if any(v is not None for v in out.values()) else 0}))
