@@ -226,6 +226,21 @@ int masr_lstm_step_f32(const float* gates_x, int64_t ldg, int64_t bstride, const
                        float* h_out_T, float* c_state, float* out, void* outh, void* outl, int64_t ld_out, int col_off,
                        const int* lens, int B, int H, int step, int reverse, void* stream);
 
+/* ---- batched chunk (streaming) state ------------------------------------------------------------ */
+
+/* Append the chunk's new rows to every slot's cache (the `torch.cat` on time of the attention K|V cache, conformer/
+ * attention.py:218-225), on the device: for slot s and t < cnt[s]
+ *   dst{0,1}[(s*cap + base[s] + t) * dst_pitch + c] = src{0,1}[(s*rows_per_slot + t) * src_pitch + col0 + c],  c < row_bytes
+ * (all sizes in BYTES, multiples of 16; src1/dst1 may both be NULL; the pair form moves the fp16 (h,l) operand halves). */
+int masr_stream_append_rows(const void* src0, const void* src1, int64_t src_pitch_bytes, int64_t col0_bytes, int row_bytes,
+                            void* dst0, void* dst1, int64_t dst_pitch_bytes, int64_t cap, const int* base, const int* cnt,
+                            int rows_per_slot, int S, void* stream);
+
+/* Slide every slot's conv-module left context (convolution.py:105-109, `new_cache = x[:, :, -lorder:]`): for slot s with
+ * n = cnt[s] > 0, rows [0, lorder) <- rows [n, n + lorder) of its [rows_per_slot, row_bytes] block of x0 (and x1). */
+int masr_stream_shift_cache(void* x0, void* x1, int64_t rows_per_slot, int lorder, int row_bytes, const int* cnt, int S,
+                            void* stream);
+
 /* ---- CTC head / greedy decode ------------------------------------------------------------------- */
 
 /* softmax statistics of CTCLoss.softmax (masr/model_utils/loss/ctc.py:70) fused with the argmax of

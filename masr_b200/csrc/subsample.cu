@@ -5,13 +5,17 @@
 //
 // Replaces GlobalCMVN.forward (utils/cmvn.py:29-31) and conv #1 + ReLU (conformer/subsampling.py:81-82,108).
 // Write-bound: 4*W1*C bytes out per (b,t) row against 3*idim*4 bytes in — one CTA per output row,
-// one thread per output channel, 1 KB coalesced stores per (t,f).
+// 8 channels per lane, 128-bit stores.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace masr {
 
+// One CTA per output row (b, t): 8 warps take the frequency positions f = warp, warp+8, ...; a lane owns 8 consecutive
+// output channels (weights in registers), so the 9 window values of a position are 9 shared-memory broadcasts for 72 FMAs
+// and the results leave as 128-bit stores (one per fp16 half, or two for fp32).  The first version (thread per channel,
+// 16-bit scalar stores, 9 shared loads per output) was instruction-bound at 75 % issue utilisation (ncu, r01).
 __global__ void __launch_bounds__(256) conv1_cmvn_relu_kernel(const float* __restrict__ feats,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ istd,
@@ -28,28 +32,47 @@ __global__ void __launch_bounds__(256) conv1_cmvn_relu_kernel(const float* __res
         s_in[i] = v;
     }
     __syncthreads();
-    for (int co = threadIdx.x; co < C; co += blockDim.x) {
-        float w[9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B = gridDim.y, TH = (F1max + 1) >> 1;
+    for (int co = lane * 8; co < C; co += 256) {          // C = 256: one pass
+        float w[8][9], bias[8];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) w[k] = __ldg(w1 + co * 9 + k);
-        const float bias = __ldg(b1 + co);
-        float* o = out ? out + (((int64_t)b * F1max + t) * W1) * C + co : nullptr;
-        const int B = gridDim.y, TH = (F1max + 1) >> 1;
-        for (int f = 0; f < W1; ++f) {
-            float acc = bias;
+        for (int j = 0; j < 8; ++j) {
+            bias[j] = __ldg(b1 + co + j);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) w[j][k] = __ldg(w1 + (co + j) * 9 + k);
+        }
+        for (int f = warp; f < W1; f += 8) {
+            float x[9];
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) acc = fmaf(w[kh * 3 + kw], s_in[kh * idim + 2 * f + kw], acc);
-            acc = fmaxf(acc, 0.f);
-            if (o) o[(int64_t)f * C] = acc;
+                for (int kw = 0; kw < 3; ++kw) x[kh * 3 + kw] = s_in[kh * idim + 2 * f + kw];
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = bias[j];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a = fmaf(w[j][k], x[k], a);          // same tap order as before (kh-major)
+                acc[j] = fmaxf(a, 0.f);
+            }
+            if (out) {
+                float* o = out + ((((int64_t)b * F1max + t) * W1) + f) * C + co;
+                *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
             if (ph) {
                 // (t,f)-parity planes [4][B][TH][20][C] for the stride-2 implicit GEMM (tc_gemm.cu)
                 const int plane = (t & 1) * 2 + (f & 1);
                 const int64_t idx = ((((int64_t)plane * B + b) * TH + (t >> 1)) * 20 + (f >> 1)) * C + co;
-                const __half hh = __float2half_rn(acc);
-                ph[idx] = hh;
-                pl[idx] = __float2half_rn((acc - __half2float(hh)) * 2048.0f);
+                __half hh[8], ll[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    hh[j] = __float2half_rn(acc[j]);
+                    ll[j] = __float2half_rn((acc[j] - __half2float(hh[j])) * 2048.0f);
+                }
+                *reinterpret_cast<uint4*>(ph + idx) = *reinterpret_cast<const uint4*>(hh);
+                *reinterpret_cast<uint4*>(pl + idx) = *reinterpret_cast<const uint4*>(ll);
             }
         }
     }
@@ -66,6 +89,7 @@ extern "C" int masr_conv1_cmvn_relu_f32(const float* feats, const float* mean, c
     MASR_REQUIRE(feats && w1 && b1 && out, "masr_conv1_cmvn_relu_f32: null pointer");
     MASR_REQUIRE((mean == nullptr) == (istd == nullptr), "masr_conv1_cmvn_relu_f32: mean/istd must both be set or both null");
     MASR_REQUIRE(2 * (F1max - 1) + 2 < Fmax && 2 * (W1 - 1) + 2 < idim, "masr_conv1_cmvn_relu_f32: window exceeds input");
+    MASR_REQUIRE(C % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "masr_conv1_cmvn_relu_f32: C must be a multiple of 8, out 16-byte aligned");
     conv1_cmvn_relu_kernel<<<dim3(F1max, B), 256, 3 * idim * sizeof(float), (cudaStream_t)stream>>>(
         feats, mean, istd, w1, b1, out, nullptr, nullptr, Fmax, idim, F1max, W1, C);
     return check_launch("conv1_cmvn_relu_kernel");
@@ -80,6 +104,8 @@ extern "C" int masr_conv1_cmvn_relu_planes_f16(const float* feats, const float* 
     MASR_REQUIRE(feats && w1 && b1 && planes_h && planes_l, "masr_conv1_cmvn_relu_planes_f16: null pointer");
     MASR_REQUIRE((mean == nullptr) == (istd == nullptr), "masr_conv1_cmvn_relu_planes_f16: mean/istd must both be set or both null");
     MASR_REQUIRE(2 * (F1max - 1) + 2 < Fmax && 2 * (W1 - 1) + 2 < idim && W1 <= 40, "masr_conv1_cmvn_relu_planes_f16: bad geometry");
+    MASR_REQUIRE(C % 8 == 0 && ((reinterpret_cast<uintptr_t>(planes_h) | reinterpret_cast<uintptr_t>(planes_l)) & 15) == 0,
+                 "masr_conv1_cmvn_relu_planes_f16: C must be a multiple of 8, planes 16-byte aligned");
     conv1_cmvn_relu_kernel<<<dim3(F1max, B), 256, 3 * idim * sizeof(float), (cudaStream_t)stream>>>(
         feats, mean, istd, w1, b1, nullptr, (__half*)planes_h, (__half*)planes_l, Fmax, idim, F1max, W1, C);
     return check_launch("conv1_cmvn_relu_kernel<planes>");

@@ -26,15 +26,115 @@ CHUNK_FRAMES = DECODING_WINDOW          # 67 feature frames -> 16 encoder frames
 CHUNK_OUT = 16
 
 
-class ConformerStreamPool:
+class _PoolBase:
+    """Shared machinery of the batched chunk-decoding pools.
+
+    Everything that varies from step to step is DEVICE DATA (one int32 table `meta`, refreshed by a single small H2D copy):
+    per slot the valid query rows, key rows and cache fill at the full and at the halved frame rate.  The launch sequence
+    of a step is therefore fixed, and after one eager step it is captured into a CUDA graph and replayed (a chunk step is
+    ~150-250 small launches: launch-bound otherwise).  K|V rows are appended and conv left contexts slid by two
+    bookkeeping kernels (csrc/stream.cu) instead of host-built index lists."""
+
+    # rows of `meta`
+    QLEN, KLEN, BASE, QLEN2, KLEN2, BASE2 = range(6)
+    OUT_ROWS = CHUNK_OUT          # output frames per slot and chunk (8 for the EfficientConformer)
+
+    def _init_common(self, eng, n_slots: int, use_graph: bool):
+        self.eng, self.S = eng, n_slots
+        dev = eng.device
+        self.meta = torch.zeros(6, n_slots, device=dev, dtype=torch.int32)
+        self.meta_host = torch.zeros(6, n_slots, dtype=torch.int32, pin_memory=True)
+        self.feats_in = torch.zeros(n_slots, CHUNK_FRAMES, 80, device=dev, dtype=torch.float32)
+        self.lens_host = [0] * n_slots
+        self.use_graph = bool(use_graph) and eng.use_graphs
+        self._graph = None
+        self._graph_launches = 0
+        self._warm = False
+        self._meta_ev = None          # the previous step's H2D copy out of `meta_host` (pinned) has completed
+
+    def _m(self, row):
+        return self.meta[row].data_ptr()
+
+    def _prepare(self, nframes: Sequence[int], short_ok_once: bool):
+        eng, S, C = self.eng, self.S, CHUNK_OUT
+        tout = [subsampled_len(int(n)) for n in nframes]
+        tout2 = [(t + 1) // 2 for t in tout]
+        for s in range(S):
+            if short_ok_once and tout[s] and self.lens_host[s] % C:
+                raise AssertionError(f"stream slot {s}: a short (final) chunk was already decoded; reset the stream first")
+            if self.lens_host[s] + tout[s] > self.cap or self.lens_host[s] + tout[s] >= eng.w.max_len:
+                raise AssertionError(f"stream slot {s}: {self.lens_host[s] + tout[s]} cached frames exceed the pool capacity")
+        if self._meta_ev is not None:
+            self._meta_ev.synchronize()
+        mh = self.meta_host.numpy()
+        mh[self.QLEN] = tout
+        mh[self.BASE] = self.lens_host
+        mh[self.KLEN] = mh[self.BASE] + mh[self.QLEN]
+        mh[self.QLEN2] = tout2
+        mh[self.BASE2] = mh[self.BASE] // 2
+        mh[self.KLEN2] = mh[self.BASE2] + mh[self.QLEN2]
+        self.meta.copy_(self.meta_host, non_blocking=True)
+        self._meta_ev = torch.cuda.Event()
+        self._meta_ev.record(torch.cuda.current_stream(eng.device))
+        return tout, tout2
+
+    def _run(self):
+        """Eager on the first step (one-time setup: function attributes, tables), then capture once and replay."""
+        eng = self.eng
+        if not self.use_graph:
+            self._body()
+            return
+        if not self._warm:
+            self._body()
+            self._warm = True
+            return
+        if self._graph is None:
+            n0 = eng.launches
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._body()
+            self._graph_launches = eng.launches - n0
+            eng.launches = n0
+            self._graph = g
+        self._graph.replay()
+        eng.launches += self._graph_launches
+
+    def _append_pair(self, src, ld_src_elems, col0_elems, ncols, dst, cap, base_row, cnt_row, rows_per_slot, elem_bytes=2):
+        """dst pair rows (s*cap + base[s] + t) <- src pair rows (s*rows_per_slot + t), columns [col0, col0+ncols)."""
+        s1, d1 = (None, None) if not isinstance(src, tuple) else (src[1], dst[1])
+        s0, d0 = (src, dst) if not isinstance(src, tuple) else (src[0], dst[0])
+        self.eng._k("stream_append", "masr_stream_append_rows", _p(s0), _p(s1), ld_src_elems * elem_bytes, col0_elems * elem_bytes,
+                    ncols * elem_bytes, _p(d0), _p(d1), d0.shape[-1] * elem_bytes, cap, self._m(base_row), self._m(cnt_row),
+                    rows_per_slot, self.S)
+
+    def _shift(self, x0, x1, rows_per_slot, lorder, row_bytes, cnt_row):
+        self.eng._k("stream_shift", "masr_stream_shift_cache", _p(x0), _p(x1), rows_per_slot, lorder, row_bytes, self._m(cnt_row), self.S)
+
+    def step(self, feats: torch.Tensor, nframes: Sequence[int]):
+        """feats [S, 67, 80] raw log-mel (device), nframes[s] = valid feature frames of slot s this round (0 = idle).
+        -> (ids [S, OUT_ROWS] int32, maxp [S, OUT_ROWS], valid output frames per slot)."""
+        tout, tout2 = self._prepare(nframes, self.SHORT_ONCE)
+        if feats.data_ptr() != self.feats_in.data_ptr():
+            self.feats_in.copy_(feats)
+        self._run()
+        for s in range(self.S):
+            self.lens_host[s] += tout[s]
+        R = self.OUT_ROWS
+        return self.b["ids"].view(self.S, R), self.b["maxp"].view(self.S, R), (tout if R == CHUNK_OUT else tout2)
+
+
+class ConformerStreamPool(_PoolBase):
     """Device state + one batched chunk step for `n_slots` streams."""
 
-    def __init__(self, eng: ConformerEngine, n_slots: int, max_frames: int = 3000):
+    SHORT_ONCE = False            # every block runs at the full frame rate: short chunks may be followed by more chunks
+
+    def __init__(self, eng: ConformerEngine, n_slots: int, max_frames: int = 3000, use_graph: bool = True):
         if not eng.causal:
             raise Exception("chunk decoding needs a streaming (causal) model")
         if eng.gemm_path != "tc":
             raise Exception("the stream pool runs on the tensor-core path")
-        self.eng, self.S, self.cap = eng, n_slots, max_frames
+        self._init_common(eng, n_slots, use_graph)
+        self.cap = max_frames
         dev, d, w = eng.device, eng.d, eng.w
         f16, f32 = torch.float16, torch.float32
         nl = len(w.layers)
@@ -46,8 +146,6 @@ class ConformerStreamPool:
         self.kv = [(torch.zeros(S * self.cap, 2 * d, device=dev, dtype=f16), torch.zeros(S * self.cap, 2 * d, device=dev, dtype=f16))
                    for _ in range(nl)]
         self.xcat = torch.zeros(nl, S, self.lorder + C, d, device=dev, dtype=f32)
-        self.lens = torch.zeros(S, device=dev, dtype=torch.int32)           # cached frames per slot (== offset)
-        self.lens_host = [0] * S
         self.b = {
             "c1p": (torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16), torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16)),
             "c2p": (torch.empty(M * eng.f2, d, device=dev, dtype=f16), torch.empty(M * eng.f2, d, device=dev, dtype=f16)),
@@ -68,26 +166,14 @@ class ConformerStreamPool:
     def reset(self, slot: int):
         """``InferencePredictor.reset_stream`` for one slot (inference_predictor.py:97-102)."""
         self.lens_host[slot] = 0
-        self.lens[slot] = 0
         self.xcat[:, slot].zero_()
 
-    def step(self, feats: torch.Tensor, nframes: Sequence[int]):
-        """feats [S, 67, 80] raw log-mel (device), nframes[s] = valid feature frames of slot s this round (0 = idle).
-        -> (ids [S,16] int32, maxp [S,16]) device tensors; the first ((n-1)//2-1)//2 entries of each row are valid."""
+    def _body(self):
+        """One batched ``forward_chunk`` over all slots (fixed launch sequence; per-slot lengths come from `meta`)."""
         eng, S, C, cap = self.eng, self.S, CHUNK_OUT, self.cap
         w, d, tw, b = eng.w, eng.d, eng._tcw, self.b
-        dev = eng.device
-        tout = [subsampled_len(int(n)) for n in nframes]
-        for s in range(S):
-            if self.lens_host[s] + tout[s] > cap or self.lens_host[s] + tout[s] >= w.max_len:
-                raise AssertionError(f"stream slot {s}: {self.lens_host[s] + tout[s]} cached frames exceed the pool capacity")
-        qlen = torch.tensor(tout, dtype=torch.int32)
-        klen = torch.tensor([self.lens_host[s] + tout[s] for s in range(S)], dtype=torch.int32)
-        b["qlen"].copy_(qlen)
-        b["klen"].copy_(klen)
-        # destination rows of the new K|V rows in the per-slot caches
-        rows = torch.tensor([s * cap + self.lens_host[s] + t for s in range(S) for t in range(tout[s])], dtype=torch.int64, device=dev)
-        src = torch.tensor([s * C + t for s in range(S) for t in range(tout[s])], dtype=torch.int64, device=dev)
+        feats = self.feats_in
+        qlen, klen = self._m(self.QLEN), self._m(self.KLEN)
         M = S * C
         F1 = (CHUNK_FRAMES - 1) // 2
         x, t0, t0p, t1p, hidp, qkv, qkvp, g, xcp = b["x"], b["t0"], b["t0p"], b["t1p"], b["hidp"], b["qkv"], b["qkvp"], b["g"], b["xcp"]
@@ -104,13 +190,11 @@ class ConformerStreamPool:
             eng._ln_split(x, L.ln_mha, t0p, M)
             eng._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, Cp=qkvp, ldc=3 * d)
             kvh, kvl = self.kv[i]
-            if rows.numel():
-                kvh.index_copy_(0, rows, qkvp[0].index_select(0, src)[:, d:])
-                kvl.index_copy_(0, rows, qkvp[1].index_select(0, src)[:, d:])
+            self._append_pair(qkvp, 3 * d, d, 2 * d, (kvh, kvl), cap, self.BASE, self.QLEN, C)      # new K|V rows -> caches
             ph, pl, _ = eng._ptab_pair(L)
             eng._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, C, kvh.data_ptr(), kvl.data_ptr(), kvh.data_ptr() + 2 * d,
                    kvl.data_ptr() + 2 * d, 2 * d, cap, _p(ph), _p(pl), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), d, C,
-                   _p(b["qlen"]), _p(b["klen"]), S, eng.h, eng.dk, C)
+                   qlen, klen, S, eng.h, eng.dk, C)
             eng._tc(t1p, d, tw[i, "wo"], L.bo, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d)
             # conv module over [cache ++ chunk] per slot (convolution.py:101-109)
             eng._ln(x, L.ln_conv, t0, M)
@@ -120,13 +204,8 @@ class ConformerStreamPool:
             eng._tc(xcp, d, tw[i, "pw1"], L.pw1_b, S * LC, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d)
             eng._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, LC, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]), None, None,
                    _p(t1p[0]), _p(t1p[1]), d, C, _p(b["clen"]), S, d, w.kernel, 0, C, 1e-5)
-            # new left context = the last `lorder` VALID rows: rows [tout, tout+lorder) of [cache ++ chunk]
-            if all(t == C for t in tout):
-                xc[:, :self.lorder].copy_(xc[:, C:C + self.lorder].clone())
-            else:
-                for s in range(S):
-                    if tout[s]:
-                        xc[s, :self.lorder].copy_(xc[s, tout[s]:tout[s] + self.lorder].clone())
+            # new left context = the last `lorder` VALID rows: rows [n, n+lorder) of [cache ++ chunk], n = valid chunk rows
+            self._shift(xc, None, LC, self.lorder, d * 4, self.QLEN)
             eng._tc(t1p, d, tw[i, "pw2"], L.pw2_b, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d)
             eng._ln_split(x, L.ln_ff, t0p, M)
             eng._tc(t0p, d, tw[i, "ff1"], L.ff[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
@@ -135,12 +214,9 @@ class ConformerStreamPool:
         eng._ln_split(x, w.after_norm, t0p, M)
         eng._tc(t0p, d, tw["ctc"], w.ctc_b, M, eng.V, d, C=b["logits"], ldc=eng.Vpad)
         eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
-        for s in range(S):
-            self.lens_host[s] += tout[s]
-        return b["ids"].view(S, C), b["maxp"].view(S, C), tout
 
 
-class SqueezeformerStreamPool:
+class SqueezeformerStreamPool(_PoolBase):
     """``ConformerStreamPool`` for the streaming Squeezeformer (``SqueezeformerEncoder.forward_chunk``,
     masr/model_utils/squeezeformer/encoder.py:240-361, with ``required_cache_size < 0`` as ``predict_stream`` passes).
 
@@ -150,10 +226,12 @@ class SqueezeformerStreamPool:
     convolution.py:119-127) is kept as the fp16 (h,l) operand pair the pointwise GEMM consumes.  A chunk shorter than 67
     frames (the last one of a stream) is supported once per stream: afterwards the slot must be reset."""
 
-    def __init__(self, eng, n_slots: int, max_frames: int = 3000):
+    SHORT_ONCE = True
+
+    def __init__(self, eng, n_slots: int, max_frames: int = 3000, use_graph: bool = True):
         if not eng.causal:
             raise Exception("chunk decoding needs a streaming (causal) model")
-        self.eng, self.S = eng, n_slots
+        self._init_common(eng, n_slots, use_graph)
         self.cap = (max_frames + 15) // 16 * 16
         self.cap2 = self.cap // 2
         dev, d, w = eng.device, eng.d, eng.w
@@ -172,7 +250,6 @@ class SqueezeformerStreamPool:
         # [cache ++ chunk] input rows of every block's conv module, as fp16 pairs
         self.xcat = [(torch.zeros(S, self.lorder + (C2 if r else C), d, device=dev, dtype=f16),
                       torch.zeros(S, self.lorder + (C2 if r else C), d, device=dev, dtype=f16)) for r in self.reduced]
-        self.lens_host = [0] * S
         self.b = {
             "c1p": (torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16), torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16)),
             "c2p": (torch.empty(M * eng.f2, d, device=dev, dtype=f16), torch.empty(M * eng.f2, d, device=dev, dtype=f16)),
@@ -199,31 +276,11 @@ class SqueezeformerStreamPool:
             xh[slot].zero_()
             xl[slot].zero_()
 
-    def step(self, feats: torch.Tensor, nframes: Sequence[int]):
-        """feats [S, 67, 80] raw log-mel (device), nframes[s] = valid feature frames of slot s this round (0 = idle).
-        -> (ids [S,16] int32, maxp [S,16], tout) — the first tout[s] = ((n-1)//2-1)//2 entries of row s are valid."""
+    def _body(self):
         eng, S, C = self.eng, self.S, CHUNK_OUT
         C2 = C // 2
         w, d, tw, b = eng.w, eng.d, eng._tcw, self.b
-        dev = eng.device
-        tout = [subsampled_len(int(n)) for n in nframes]
-        tout2 = [(t + 1) // 2 for t in tout]
-        for s in range(S):
-            if tout[s] and self.lens_host[s] % C:
-                raise AssertionError(f"stream slot {s}: a short (final) chunk was already decoded; reset the stream first")
-            if self.lens_host[s] + tout[s] > self.cap or self.lens_host[s] + tout[s] >= w.max_len:
-                raise AssertionError(f"stream slot {s}: {self.lens_host[s] + tout[s]} cached frames exceed the pool capacity")
-        b["qlen"].copy_(torch.tensor(tout, dtype=torch.int32))
-        b["klen"].copy_(torch.tensor([self.lens_host[s] + tout[s] for s in range(S)], dtype=torch.int32))
-        b["qlen2"].copy_(torch.tensor(tout2, dtype=torch.int32))
-        b["klen2"].copy_(torch.tensor([self.lens_host[s] // 2 + tout2[s] for s in range(S)], dtype=torch.int32))
-
-        def scatter(cap, base, cnt, stride):
-            rows = torch.tensor([s * cap + base[s] + t for s in range(S) for t in range(cnt[s])], dtype=torch.int64, device=dev)
-            src = torch.tensor([s * stride + t for s in range(S) for t in range(cnt[s])], dtype=torch.int64, device=dev)
-            return rows, src
-        sc_full = scatter(self.cap, self.lens_host, tout, C)
-        sc_half = scatter(self.cap2, [n // 2 for n in self.lens_host], tout2, C2)
+        feats = self.feats_in
         M, M2 = S * C, S * C2
         F1 = (CHUNK_FRAMES - 1) // 2
         x, y, saved, t0p, t1p, hidp, qkv, qkvp, g = (b["x"], b["y"], b["saved"], b["t0p"], b["t1p"], b["hidp"], b["qkv"],
@@ -235,33 +292,32 @@ class SqueezeformerStreamPool:
         eng._tc(b["c2p"], eng.f2 * d, tw["embed"], w.embed_b, M, d, eng.f2 * d, EPI_BIAS, C=y, ldc=d)
         eng._ln_ada(y, w.preln, x, w.layers[0].att_ada, t0p, M)
         nl = len(w.layers)
-        Mi, Ci, qlen, klen, clen, sc, cap = M, C, b["qlen"], b["klen"], b["clen"], sc_full, self.cap
+        full = (M, C, self.QLEN, self.KLEN, self.BASE, b["clen"], self.cap)
+        half = (M2, C2, self.QLEN2, self.KLEN2, self.BASE2, b["clen2"], self.cap2)
+        Mi, Ci, rq, rk, rb, clen, cap = full
         for i, L in enumerate(w.layers):
             if i == eng.REDUCE:
                 saved.copy_(x)
                 eng._k("time_reduce", "masr_time_reduce_dw_split_f16", _p(x), C, _p(w.tr_dw), _p(w.tr_dw_b), _p(t1p[0]), _p(t1p[1]),
-                       C2, _p(b["qlen"]), S, C2, int(w.tr_dw.shape[1]), 0, d)
+                       C2, self._m(self.QLEN), S, C2, int(w.tr_dw.shape[1]), 0, d)
                 eng._tc(t1p, d, tw["tr_pw"], w.tr_pw_b, M2, d, d, EPI_BIAS, C=x, ldc=d)
                 eng._k("affine_split", "masr_affine_split_f16", _p(x), _p(L.att_ada[0]), _p(L.att_ada[1]), _p(t0p[0]), _p(t0p[1]), M2, d)
-                Mi, Ci, qlen, klen, clen, sc, cap = M2, C2, b["qlen2"], b["klen2"], b["clen2"], sc_half, self.cap2
+                Mi, Ci, rq, rk, rb, clen, cap = half
             if i == eng.RECOVER:
                 eng._k("affine_split", "masr_affine_split_f16", _p(x), None, None, _p(t1p[0]), _p(t1p[1]), M2, d)
                 eng._tc(t1p, d, tw["rec"], w.rec_b, M2, d, d, EPI_BIAS, C=y, ldc=d)
                 eng._k("upsample_add", "masr_upsample2_add_f32", _p(saved), _p(y), _p(x), C, C2, S, C, d)
-                Mi, Ci, qlen, klen, clen, sc, cap = M, C, b["qlen"], b["klen"], b["clen"], sc_full, self.cap
+                Mi, Ci, rq, rk, rb, clen, cap = full
                 eng._k("affine_split", "masr_affine_split_f16", _p(x), _p(L.att_ada[0]), _p(L.att_ada[1]), _p(t0p[0]), _p(t0p[1]), Mi, d)
             LCi = self.lorder + Ci
             # MHA over [cache ++ chunk] keys
             eng._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, Cp=qkvp, ldc=3 * d)
             kvh, kvl = self.kv[i]
-            rows, src = sc
-            if rows.numel():
-                kvh.index_copy_(0, rows, qkvp[0][:Mi].index_select(0, src)[:, d:])
-                kvl.index_copy_(0, rows, qkvp[1][:Mi].index_select(0, src)[:, d:])
+            self._append_pair(qkvp, 3 * d, d, 2 * d, (kvh, kvl), cap, rb, rq, Ci)
             ph, pl, _ = eng._ptab_pair(L)
             eng._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, Ci, kvh.data_ptr(), kvl.data_ptr(), kvh.data_ptr() + 2 * d,
                    kvl.data_ptr() + 2 * d, 2 * d, cap, _p(ph), _p(pl), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), d, Ci,
-                   _p(qlen), _p(klen), S, eng.h, eng.dk, Ci)
+                   self._m(rq), self._m(rk), S, eng.h, eng.dk, Ci)
             eng._tc(t1p, d, tw[i, "wo"], L.bo, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=y, ldc=d)
             eng._ln_ada(y, L.ln1, x, L.ffn1_ada, t0p, Mi)
             eng._tc(t0p, d, tw[i, "f1a"], L.ffn1[1], Mi, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
@@ -275,15 +331,7 @@ class SqueezeformerStreamPool:
             eng._k("dwconv_bn_silu", "masr_dwconv_bn_silu_f32", _p(g), d, LCi, _p(L.dw), _p(L.dw_b), _p(L.bn[0]), _p(L.bn[1]), None,
                    None, _p(t1p[0]), _p(t1p[1]), d, Ci, _p(clen), S, d, L.kernel, 0, Ci)
             # new left context = the last `lorder` VALID rows: rows [n, n + lorder) of [cache ++ chunk], n = valid chunk rows
-            cnt = tout if Ci == C else tout2
-            if all(t == Ci for t in cnt):
-                xh[:, :self.lorder].copy_(xh[:, Ci:Ci + self.lorder].clone())
-                xl[:, :self.lorder].copy_(xl[:, Ci:Ci + self.lorder].clone())
-            else:
-                for s in range(S):
-                    if cnt[s]:
-                        xh[s, :self.lorder].copy_(xh[s, cnt[s]:cnt[s] + self.lorder].clone())
-                        xl[s, :self.lorder].copy_(xl[s, cnt[s]:cnt[s] + self.lorder].clone())
+            self._shift(xh, xl, LCi, self.lorder, d * 2, rq)
             eng._tc(t1p, d, tw[i, "pw2"], L.pw2_b, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=y, ldc=d)
             eng._ln_ada(y, L.ln3, x, L.ffn2_ada, t0p, Mi)
             eng._tc(t0p, d, tw[i, "f2a"], L.ffn2[1], Mi, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
@@ -292,12 +340,9 @@ class SqueezeformerStreamPool:
             eng._ln_ada(y, L.ln4, x, nxt, t0p, Mi)       # last block: pair(x) feeds the CTC head
         eng._tc(t0p, d, tw["ctc"], w.ctc_b, M, eng.V, d, C=b["logits"], ldc=eng.Vpad)
         eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
-        for s in range(S):
-            self.lens_host[s] += tout[s]
-        return b["ids"].view(S, C), b["maxp"].view(S, C), tout
 
 
-class EfficientConformerStreamPool:
+class EfficientConformerStreamPool(_PoolBase):
     """Batched chunk decoding for the streaming EfficientConformer (``EfficientConformerEncoder.forward_chunk``,
     masr/model_utils/efficient_conformer/encoder.py:267-392, ``required_cache_size < 0``).
 
@@ -308,10 +353,13 @@ class EfficientConformerStreamPool:
     output frames and is doubled inside (:306).  One chunk yields 8 output frames.  A short final chunk is supported once
     per stream (reset afterwards)."""
 
-    def __init__(self, eng, n_slots: int, max_frames: int = 3000):
+    SHORT_ONCE = True
+    OUT_ROWS = CHUNK_OUT // 2
+
+    def __init__(self, eng, n_slots: int, max_frames: int = 3000, use_graph: bool = True):
         if not eng.causal:
             raise Exception("chunk decoding needs a streaming (causal) model")
-        self.eng, self.S = eng, n_slots
+        self._init_common(eng, n_slots, use_graph)
         self.cap = (max_frames + 15) // 16 * 16
         self.cap2 = self.cap // 2
         dev, d, w = eng.device, eng.d, eng.w
@@ -329,7 +377,6 @@ class EfficientConformerStreamPool:
         self.xcat = [(torch.zeros(S, (L.kernel - 1) + (C if i <= self.SL else C2), d, device=dev, dtype=f16),
                       torch.zeros(S, (L.kernel - 1) + (C if i <= self.SL else C2), d, device=dev, dtype=f16))
                      for i, L in enumerate(w.layers)]
-        self.lens_host = [0] * S
         LCmax = max(x[0].shape[1] for x in self.xcat)
         self.b = {
             "c1p": (torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16), torch.zeros(4 * S * TH * 20 * d, device=dev, dtype=f16)),
@@ -355,31 +402,11 @@ class EfficientConformerStreamPool:
             xh[slot].zero_()
             xl[slot].zero_()
 
-    def step(self, feats: torch.Tensor, nframes: Sequence[int]):
-        """feats [S, 67, 80] raw log-mel (device), nframes[s] = valid feature frames of slot s (0 = idle).
-        -> (ids [S,8] int32, maxp [S,8], tout) with tout[s] = ceil((((n-1)//2-1)//2) / 2) valid output frames."""
+    def _body(self):
         eng, S, C = self.eng, self.S, CHUNK_OUT
         C2 = C // 2
         w, d, tw, b = eng.w, eng.d, eng._tcw, self.b
-        dev = eng.device
-        tout = [subsampled_len(int(n)) for n in nframes]
-        tout2 = [(t + 1) // 2 for t in tout]
-        for s in range(S):
-            if tout[s] and self.lens_host[s] % C:
-                raise AssertionError(f"stream slot {s}: a short (final) chunk was already decoded; reset the stream first")
-            if self.lens_host[s] + tout[s] > self.cap or self.lens_host[s] + tout[s] >= w.max_len:
-                raise AssertionError(f"stream slot {s}: {self.lens_host[s] + tout[s]} cached frames exceed the pool capacity")
-        b["qlen"].copy_(torch.tensor(tout, dtype=torch.int32))
-        b["klen"].copy_(torch.tensor([self.lens_host[s] + tout[s] for s in range(S)], dtype=torch.int32))
-        b["qlen2"].copy_(torch.tensor(tout2, dtype=torch.int32))
-        b["klen2"].copy_(torch.tensor([self.lens_host[s] // 2 + tout2[s] for s in range(S)], dtype=torch.int32))
-
-        def scatter(cap, base, cnt, stride):
-            rows = torch.tensor([s * cap + base[s] + t for s in range(S) for t in range(cnt[s])], dtype=torch.int64, device=dev)
-            src = torch.tensor([s * stride + t for s in range(S) for t in range(cnt[s])], dtype=torch.int64, device=dev)
-            return rows, src
-        sc_full = scatter(self.cap, self.lens_host, tout, C)
-        sc_half = scatter(self.cap2, [n // 2 for n in self.lens_host], tout2, C2)
+        feats = self.feats_in
         M, M2 = S * C, S * C2
         F1 = (CHUNK_FRAMES - 1) // 2
         x, t0, t0p, t1p, hidp, qkv, qkvp, g, qb, kvn = (b["x"], b["t0"], b["t0p"], b["t1p"], b["hidp"], b["qkv"], b["qkvp"],
@@ -392,8 +419,7 @@ class EfficientConformerStreamPool:
         for i, L in enumerate(w.layers):
             half = i > self.SL
             Mi, Ci = (M2, C2) if half else (M, C)
-            qlen, klen = (b["qlen2"], b["klen2"]) if half else (b["qlen"], b["klen"])
-            rows, src = sc_half if half else sc_full
+            rq, rk, rb = (self.QLEN2, self.KLEN2, self.BASE2) if half else (self.QLEN, self.KLEN, self.BASE)
             cap = self.cap2 if half else self.cap
             lorder = L.kernel - 1
             LCi = lorder + Ci
@@ -406,21 +432,18 @@ class EfficientConformerStreamPool:
                 eng._tc(t0p, d, (wh[:d], wl[:d]), L.bqkv[:d], Mi, d, d, C=qb, ldc=d)
                 eng._tc(t0p, d, (wh[d:], wl[d:]), L.bqkv[d:], Mi, 2 * d, d, C=kvn, ldc=2 * d)
                 kc = self.kv32[i]
-                if rows.numel():
-                    kc.index_copy_(0, rows, kvn.index_select(0, src))
+                self._append_pair(kvn, 2 * d, 0, 2 * d, kc, cap, rb, rq, Ci, elem_bytes=4)
                 eng._k("attention", "masr_grouped_attention_cache_f32", _p(qb), d, Ci, kc.data_ptr(), kc.data_ptr() + 4 * d, 2 * d, cap,
-                       _p(L.ptab), _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), _p(qlen), _p(klen), S, eng.h, eng.dk,
+                       _p(L.ptab), _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), self._m(rq), self._m(rk), S, eng.h, eng.dk,
                        eng.GROUP, Ci)
             else:
                 eng._tc(t0p, d, tw[i, "qkv"], L.bqkv, Mi, 3 * d, d, C=qkv, Cp=qkvp, ldc=3 * d)
                 kvh, kvl = self.kv[i]
-                if rows.numel():
-                    kvh.index_copy_(0, rows, qkvp[0][:Mi].index_select(0, src)[:, d:])
-                    kvl.index_copy_(0, rows, qkvp[1][:Mi].index_select(0, src)[:, d:])
+                self._append_pair(qkvp, 3 * d, d, 2 * d, (kvh, kvl), cap, rb, rq, Ci)
                 ph, pl, _ = eng._ptab_pair(L)
                 eng._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, Ci, kvh.data_ptr(), kvl.data_ptr(), kvh.data_ptr() + 2 * d,
                        kvl.data_ptr() + 2 * d, 2 * d, cap, _p(ph), _p(pl), d, _p(L.pos_u), _p(L.pos_v), None, _p(t1p[0]), _p(t1p[1]), d, Ci,
-                       _p(qlen), _p(klen), S, eng.h, eng.dk, Ci)
+                       self._m(rq), self._m(rk), S, eng.h, eng.dk, Ci)
             eng._tc(t1p, d, tw[i, "wo"], L.bo, Mi, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d)
             # conv module over [cache ++ chunk] per slot (convolution.py:93-111)
             eng._ln_split(x, L.ln_conv, t0p, Mi)
@@ -428,25 +451,17 @@ class EfficientConformerStreamPool:
             xh[:, lorder:].copy_(t0p[0][:Mi].view(S, Ci, d))
             xl[:, lorder:].copy_(t0p[1][:Mi].view(S, Ci, d))
             eng._tc((xh, xl), d, tw[i, "pw1"], L.pw1_b, S * LCi, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d)
-            cnt = tout2 if half else tout
             if i == self.SL:
                 eng._k("dwconv_ln_silu", "masr_dwconv_ln_silu_strided_f32", _p(g), d, LCi, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]),
                        None, None, _p(t1p[0]), _p(t1p[1]), d, C2, _p(b["clen"]), S, d, L.kernel, 0, 2, C2, 1e-5)
-                eng._k("avgpool", "masr_avgpool2_time_f32", _p(x), C, _p(t0), C2, _p(b["qlen"]), S, C2, d)
+                eng._k("avgpool", "masr_avgpool2_time_f32", _p(x), C, _p(t0), C2, self._m(self.QLEN), S, C2, d)
                 Mo, res = M2, t0
             else:
                 eng._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, LCi, _p(L.dw), _p(L.dw_b), _p(L.cn[0]), _p(L.cn[1]), None,
                        None, _p(t1p[0]), _p(t1p[1]), d, Ci, _p(b["clen"]), S, d, L.kernel, 0, Ci, 1e-5)
                 Mo, res = Mi, x
             # new left context = the last `lorder` VALID rows of [cache ++ chunk]
-            if all(t == Ci for t in cnt):
-                xh[:, :lorder].copy_(xh[:, Ci:Ci + lorder].clone())
-                xl[:, :lorder].copy_(xl[:, Ci:Ci + lorder].clone())
-            else:
-                for s in range(S):
-                    if cnt[s]:
-                        xh[s, :lorder].copy_(xh[s, cnt[s]:cnt[s] + lorder].clone())
-                        xl[s, :lorder].copy_(xl[s, cnt[s]:cnt[s] + lorder].clone())
+            self._shift(xh, xl, LCi, lorder, d * 2, rq)
             eng._tc(t1p, d, tw[i, "pw2"], L.pw2_b, Mo, d, d, EPI_RESIDUAL, 1.0, res, d, C=x, ldc=d)
             eng._ln_split(x, L.ln_ff, t0p, Mo)
             eng._tc(t0p, d, tw[i, "ff1"], L.ff[1], Mo, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn)
@@ -455,9 +470,6 @@ class EfficientConformerStreamPool:
         eng._ln_split(x, w.after_norm, t0p, M2)
         eng._tc(t0p, d, tw["ctc"], w.ctc_b, M2, eng.V, d, C=b["logits"], ldc=eng.Vpad)
         eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M2, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
-        for s in range(S):
-            self.lens_host[s] += tout[s]
-        return b["ids"].view(S, C2), b["maxp"].view(S, C2), tout2
 
 
 class PoolStream:
