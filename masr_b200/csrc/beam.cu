@@ -6,7 +6,11 @@
 //                          where the cumulative probability reaches `cutoff_prob`; emits ids + log-probabilities.
 //                          The [T,V] posterior never goes to the host (the reference ships it as Python lists).
 //   prefix_beam_kernel     one CTA per utterance walks the frames; the beam lives in shared memory, the prefix trie
-//                          (parent, token) in global memory; selection = exact radix select + bitonic sort, so ties
+//                          (parent, token) plus a persistent (parent, token) -> node hash in global memory, so a prefix that
+//                          drops out of the beam and is re-created later keeps its identity (and its children in the beam
+//                          keep merging with it) exactly like the restatement's `child` dictionary — without it two beam
+//                          entries could spell the same prefix and split its mass (seen as a ln 2 score gap on a 12 s
+//                          utterance); selection = exact radix select + bitonic sort, so ties
 //                          resolve deterministically (existing prefixes by rank, then children in (parent rank, candidate)
 //                          order) and the result equals the CPU restatement.
 #include <math.h>
@@ -141,6 +145,12 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
     float* pool = pool_all + (int64_t)b * (BEAM_CAP + BEAM_CAP * BK_MAX);
     int* tpar = trie_parent + (int64_t)b * trie_cap;
     int* ttok = trie_tok + (int64_t)b * trie_cap;
+    // per-utterance trie storage: [0, node_cap) nodes, then in `trie_parent` an open-addressing hash of node ids keyed by
+    // (parent, token) (4 slots per possible node; compared through tpar/ttok of the stored id)
+    const int64_t node_cap = trie_cap / 5;
+    const uint32_t hcap = (uint32_t)(trie_cap - node_cap);
+    int* thash = tpar + node_cap;
+    for (int64_t i = tid; i < hcap; i += BEAM_THREADS) thash[i] = -1;
     int nbeam = 1, nnodes = 1;
     if (tid == 0) {
         S.node[0] = 0; S.par[0] = -1; S.last[0] = -1; S.pb[0] = 0.f; S.pnb[0] = -INFINITY; S.score[0] = 0.f;
@@ -297,15 +307,40 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
             }
         }
         __syncthreads();
-        if (tid == 0) {                               // node ids in rank order (deterministic)
-            for (int r = 0; r < n_sel; ++r)
-                if (S.s_src[r] == 1) {
-                    const int id = nnodes++;
-                    if (id < trie_cap) { tpar[id] = S.s_par[r]; ttok[id] = S.s_last[r]; }
-                    S.s_node[r] = id;
-                }
-            S.misc[4] = nnodes;
+        // new children: reuse the node of a prefix that existed before (persistent hash), else allocate ids in rank order
+        int need_new = 0;
+        if (tid < n_sel && S.s_src[tid] == 1) {
+            const int par = S.s_par[tid], tok = S.s_last[tid];
+            uint32_t h = (((uint32_t)par * 2654435761u) ^ ((uint32_t)tok * 40503u)) % hcap;
+            int found = -1;
+            for (;;) {
+                const int id = thash[h];
+                if (id == -1) break;
+                if (tpar[id] == par && ttok[id] == tok) { found = id; break; }
+                h = h + 1 == hcap ? 0 : h + 1;
+            }
+            S.s_node[tid] = found;
+            need_new = found < 0;
         }
+        S.scan[tid] = need_new;
+        __syncthreads();
+        for (int off = 1; off < BEAM_THREADS; off <<= 1) {
+            int v = tid >= off ? S.scan[tid - off] : 0;
+            __syncthreads();
+            S.scan[tid] += v;
+            __syncthreads();
+        }
+        if (need_new) {
+            const int id = nnodes + S.scan[tid] - 1;          // rank order (deterministic)
+            S.s_node[tid] = id;
+            if (id < node_cap) {
+                const int par = S.s_par[tid], tok = S.s_last[tid];
+                tpar[id] = par; ttok[id] = tok;
+                uint32_t h = (((uint32_t)par * 2654435761u) ^ ((uint32_t)tok * 40503u)) % hcap;
+                while (atomicCAS(&thash[h], -1, id) != -1) h = h + 1 == hcap ? 0 : h + 1;
+            }
+        }
+        if (tid == BEAM_THREADS - 1) S.misc[4] = nnodes + S.scan[tid];
         __syncthreads();
         nnodes = S.misc[4];
         if (tid < n_sel) {
@@ -323,10 +358,10 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
             sc = S.score[0];
             int node = S.node[0];
             int len = 0;
-            for (int x = node; x > 0 && x < trie_cap; x = tpar[x]) ++len;
+            for (int x = node; x > 0 && x < node_cap; x = tpar[x]) ++len;
             n = len;
             int pos = len - 1;
-            for (int x = node; x > 0 && x < trie_cap && pos >= 0; x = tpar[x]) out_tok[(int64_t)b * tok_stride + pos--] = ttok[x];
+            for (int x = node; x > 0 && x < node_cap && pos >= 0; x = tpar[x]) out_tok[(int64_t)b * tok_stride + pos--] = ttok[x];
         }
         out_n[b] = n;
         out_score[b] = sc;
@@ -350,7 +385,7 @@ extern "C" int masr_ctc_topk_f32(const float* logits, int64_t ldl, int M, int V,
 extern "C" int masr_ctc_prefix_beam_workspace(int B, int Tmax, int64_t* pool_floats, int64_t* trie_ints_per_utt) {
     MASR_REQUIRE(pool_floats && trie_ints_per_utt, "masr_ctc_prefix_beam_workspace: null pointer");
     *pool_floats = (int64_t)B * (BEAM_CAP + BEAM_CAP * BK_MAX);
-    *trie_ints_per_utt = (int64_t)Tmax * BEAM_CAP + 1;
+    *trie_ints_per_utt = 5 * ((int64_t)Tmax * BEAM_CAP + 1);      // nodes + 4 hash slots per possible node
     return MASR_OK;
 }
 

@@ -35,7 +35,7 @@ constexpr int kSumChunk = 8192;
 
 struct FbankTables {
     float window[kFrameLen];
-    float2 twiddle[kHalf / 2];      // exp(-2*pi*i*k/256)
+    float2 twiddle[kHalf];          // exp(-2*pi*i*k/256), k = 0..255 (full circle)
     float2 post[kHalf + 1];         // exp(-2*pi*i*k/512), k = 0..256
     int mel_start[kMel];
     int mel_len[kMel];
@@ -59,7 +59,7 @@ static void build_tables() {
         float hann = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / (kFrameLen - 1)));
         h.window[i] = powf(hann, 0.85f);
     }
-    for (int k = 0; k < kHalf / 2; ++k) {
+    for (int k = 0; k < kHalf; ++k) {
         double a = -2.0 * M_PI * k / kHalf;
         h.twiddle[k] = make_float2((float)cos(a), (float)sin(a));
     }
@@ -148,23 +148,80 @@ __global__ void wave_gain_kernel(const int64_t* __restrict__ offs, const double*
 }
 
 // ---- fbank ----------------------------------------------------------------------------------------
+// One warp per frame.  The 512-point real FFT runs as a 256-point complex FFT factored 8 x 8 x 4 (decimation in
+// frequency): each lane keeps 8 complex points in registers and does the radix-8 / radix-4 butterflies there, so the data
+// crosses shared memory twice (two transposes) instead of once per radix-2 stage — the first version (8 radix-2 stages in
+// shared memory, twiddles and window through L1) ran at 91 % L1/shared-pipe utilisation and 0.04 of the HBM roofline
+// (ncu, profiles/r01_step_kernels_summary.md).  Stage twiddles live in registers, window / post-twiddles / mel weights in
+// shared memory (loaded once per CTA).
 constexpr int kWarpsPerBlock = 4;
-constexpr int kFramesPerWarp = 2;
+constexpr int kFramesPerWarp = 4;
+constexpr int kQStride = 36;                 // float2 pitch of a 32-point block in the FFT scratch: conflict-free stage 2
+
+struct cpx { float x, y; };
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cpx cmul(cpx a, float2 w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
+__device__ __forceinline__ cpx mul_mi(cpx a) { return {a.y, -a.x}; }            // * (-i)
+
+// r[s] = sum_m c[m] * exp(-2 pi i m s / 4)
+__device__ __forceinline__ void dft4(const cpx (&c)[4], cpx (&r)[4]) {
+    const cpx d0 = cadd(c[0], c[2]), d1 = csub(c[0], c[2]), d2 = cadd(c[1], c[3]), d3 = mul_mi(csub(c[1], c[3]));
+    r[0] = cadd(d0, d2); r[2] = csub(d0, d2); r[1] = cadd(d1, d3); r[3] = csub(d1, d3);
+}
+// o[q] = sum_j a[j] * exp(-2 pi i j q / 8)
+__device__ __forceinline__ void dft8(const cpx (&a)[8], cpx (&o)[8]) {
+    constexpr float S = 0.70710678118654752440f;
+    cpx e[4], f[4];
+    e[0] = cadd(a[0], a[4]); e[1] = cadd(a[1], a[5]); e[2] = cadd(a[2], a[6]); e[3] = cadd(a[3], a[7]);
+    const cpx t0 = csub(a[0], a[4]), t1 = csub(a[1], a[5]), t2 = csub(a[2], a[6]), t3 = csub(a[3], a[7]);
+    f[0] = t0;
+    f[1] = {S * (t1.x + t1.y), S * (t1.y - t1.x)};      // * W8
+    f[2] = mul_mi(t2);                                   // * W8^2
+    f[3] = {S * (t3.y - t3.x), -S * (t3.x + t3.y)};     // * W8^3
+    cpx re[4], ro[4];
+    dft4(e, re);
+    dft4(f, ro);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { o[2 * r] = re[r]; o[2 * r + 1] = ro[r]; }
+}
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) fbank_kernel(
     const float* __restrict__ wave, const int64_t* __restrict__ offs, const float* __restrict__ gain,
     float* __restrict__ feats, int* __restrict__ nframes_out, int Fmax) {
-    __shared__ float2 s_z[kWarpsPerBlock][kHalf + 1];      // FFT work area (+1: Z[256] alias slot)
-    __shared__ float s_p[kWarpsPerBlock][kFrameLen];      // frame samples, later the power spectrum P[0..256]
+    __shared__ __align__(16) float2 s_z[kWarpsPerBlock][8 * kQStride];   // FFT scratch, then Z[0..256] in natural order
+    __shared__ float s_p[kWarpsPerBlock][kHalf + 4];                      // power spectrum P[0..256]
+    __shared__ float s_win[kFrameLen];
+    __shared__ float2 s_post[kHalf + 1];
+    __shared__ float s_melw[kMaxMelW];
 
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < kFrameLen; i += kWarpsPerBlock * 32) s_win[i] = __ldg(&g_tab.window[i]);
+    for (int i = threadIdx.x; i <= kHalf; i += kWarpsPerBlock * 32) s_post[i] = __ldg(&g_tab.post[i]);
+    for (int i = threadIdx.x; i < kMaxMelW; i += kWarpsPerBlock * 32) s_melw[i] = __ldg(&g_tab.mel_w[i]);
+    __syncthreads();
     const int64_t beg = offs[b], n = offs[b + 1] - beg;
     const int F = n < kFrameLen ? 0 : 1 + (int)((n - kFrameLen) / kFrameShift);
     if (blockIdx.x == 0 && threadIdx.x == 0 && nframes_out) nframes_out[b] = F;
     const float g = gain ? gain[b] : 1.f;
     float2* z = s_z[warp];
     float* pw = s_p[warp];
+    // per-lane constants: stage twiddles W256^(lane*q) and W32^((lane&3)*p), mel bins lane, lane+32, lane+64
+    float2 tw1[8], tw2[8];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+        tw1[q] = __ldg(&g_tab.twiddle[(lane * q) & 255]);
+        tw2[q] = __ldg(&g_tab.twiddle[(8 * (lane & 3) * q) & 255]);
+    }
+    int mst[3], mln[3], mof[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int m = lane + 32 * r;
+        mst[r] = m < kMel ? __ldg(&g_tab.mel_start[m]) : 0;
+        mln[r] = m < kMel ? __ldg(&g_tab.mel_len[m]) : 0;
+        mof[r] = m < kMel ? __ldg(&g_tab.mel_off[m]) : 0;
+    }
 
     for (int fi = 0; fi < kFramesPerWarp; ++fi) {
         const int f = (blockIdx.x * kWarpsPerBlock + warp) * kFramesPerWarp + fi;
@@ -175,65 +232,88 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) fbank_kernel(
             continue;
         }
         const float* src = wave + beg + (int64_t)f * kFrameShift;
-        // 1. load + quantise (audio.py:264,566-574: fl(x*g), *2^15, clip, truncate) and frame mean
-        float q[13];
+        // 1. load + quantise (audio.py:264,566-574: fl(x*g), *2^15, clip, truncate): lane holds the sample pairs
+        //    (2c, 2c+1), c = lane + 32 j — exactly the complex points its radix-8 butterfly needs.  The frame sum is a sum
+        //    of integers below 2^24, exact in float32 in any order.
+        float x0[8], x1[8];
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            int i = lane + 32 * j;
-            float v = 0.f;
-            if (i < kFrameLen) {
-                v = __ldg(src + i) * g;
-                v = v * 32768.0f;
-                v = fminf(fmaxf(v, -32768.0f), 32767.0f);
-                v = truncf(v);
+        for (int j = 0; j < 8; ++j) {
+            const int i0 = 2 * (lane + 32 * j);
+            float v0 = 0.f, v1 = 0.f;
+            if (i0 < kFrameLen) {
+                v0 = __ldg(src + i0) * g;
+                v0 = truncf(fminf(fmaxf(v0 * 32768.0f, -32768.0f), 32767.0f));
+                v1 = __ldg(src + i0 + 1) * g;
+                v1 = truncf(fminf(fmaxf(v1 * 32768.0f, -32768.0f), 32767.0f));
             }
-            q[j] = v;
-            sum += v;
+            x0[j] = v0; x1[j] = v1;
+            sum += v0 + v1;
         }
         sum = warp_sum(sum);
         const float mean = sum / (float)kFrameLen;         // kaldi.py:183-186
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            int i = lane + 32 * j;
-            if (i < kFrameLen) pw[i] = q[j] - mean;
-        }
-        __syncwarp();
-        // 2. pre-emphasis (replicate-left), window, pack even/odd samples into complex points,
-        //    stored bit-reversed for the in-place radix-2 DIT FFT
+        // 2. DC removal, pre-emphasis (replicate-left), povey window -> complex points (re, im) = (s[2c], s[2c+1])
+        cpx a[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            int c = lane + 32 * j;                         // complex point index 0..255
-            int i0 = 2 * c, i1 = 2 * c + 1;
-            float re = 0.f, im = 0.f;
-            if (i0 < kFrameLen) {
-                float cur = pw[i0], prev = pw[i0 > 0 ? i0 - 1 : 0];
-                re = (cur - 0.97f * prev) * __ldg(&g_tab.window[i0]);
-                float cur1 = pw[i1];
-                im = (cur1 - 0.97f * cur) * __ldg(&g_tab.window[i1]);
+            const int i0 = 2 * (lane + 32 * j);
+            const bool ok = i0 < kFrameLen;
+            const float c0 = x0[j] - mean, c1 = x1[j] - mean;
+            // previous sample of s[2c] is s[2c-1]: the odd sample of lane-1 (same j), or of lane 31 one j earlier
+            float pv = __shfl_up_sync(0xffffffffu, c1, 1);
+            const float pw31 = __shfl_sync(0xffffffffu, j > 0 ? x1[j > 0 ? j - 1 : 0] - mean : 0.f, 31);
+            if (lane == 0) pv = j == 0 ? c0 : pw31;
+            a[j].x = ok ? (c0 - 0.97f * pv) * s_win[ok ? i0 : 0] : 0.f;
+            a[j].y = ok ? (c1 - 0.97f * c0) * s_win[ok ? i0 + 1 : 0] : 0.f;
+        }
+        // 3. 256-point complex FFT, 8 x 8 x 4
+        {
+            cpx y[8];
+            dft8(a, y);                                    // over j (points lane + 32 j)
+            z[lane] = make_float2(y[0].x, y[0].y);
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                const cpx t = cmul(y[q], tw1[q]);
+                z[kQStride * q + lane] = make_float2(t.x, t.y);
             }
-            z[__brev((unsigned)c) >> 24] = make_float2(re, im);
         }
         __syncwarp();
-        // 3. 256-point complex FFT, 8 radix-2 stages, 4 butterflies per lane per stage
+        {
+            const int q = lane >> 2, m = lane & 3;
+            float2* zq = z + kQStride * q + m;
+            cpx u[8], v[8];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const int half = 1 << s;
+            for (int j = 0; j < 8; ++j) { const float2 t = zq[4 * j]; u[j] = {t.x, t.y}; }
+            dft8(u, v);                                    // over j' (points m + 4 j' of block q)
+            zq[0] = make_float2(v[0].x, v[0].y);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                int j = lane + 32 * r;                     // butterfly 0..127
-                int pos = j & (half - 1);
-                int i0 = ((j >> s) << (s + 1)) + pos;
-                int i1 = i0 + half;
-                float2 w = __ldg(&g_tab.twiddle[pos << (7 - s)]);
-                float2 a = z[i0], bb = z[i1];
-                float tr = bb.x * w.x - bb.y * w.y;
-                float ti = bb.x * w.y + bb.y * w.x;
-                z[i0] = make_float2(a.x + tr, a.y + ti);
-                z[i1] = make_float2(a.x - tr, a.y - ti);
+            for (int pp = 1; pp < 8; ++pp) {
+                const cpx t = cmul(v[pp], tw2[pp]);
+                zq[4 * pp] = make_float2(t.x, t.y);
             }
-            __syncwarp();
         }
+        __syncwarp();
+        {
+            const int q = lane & 7, ph = lane >> 3;
+            cpx r0[4], r1[4];
+            {
+                cpx c0[4], c1[4];
+                const float4* p0 = reinterpret_cast<const float4*>(z + kQStride * q + 4 * ph);
+                const float4* p1 = reinterpret_cast<const float4*>(z + kQStride * q + 4 * (ph + 4));
+                const float4 a0 = p0[0], a1 = p0[1], b0 = p1[0], b1 = p1[1];
+                c0[0] = {a0.x, a0.y}; c0[1] = {a0.z, a0.w}; c0[2] = {a1.x, a1.y}; c0[3] = {a1.z, a1.w};
+                c1[0] = {b0.x, b0.y}; c1[1] = {b0.z, b0.w}; c1[2] = {b1.x, b1.y}; c1[3] = {b1.z, b1.w};
+                dft4(c0, r0);
+                dft4(c1, r1);
+            }
+            __syncwarp();                                  // every lane has read its inputs: reuse the scratch for Z[k]
+#pragma unroll
+            for (int sI = 0; sI < 4; ++sI) {
+                z[q + 8 * ph + 64 * sI] = make_float2(r0[sI].x, r0[sI].y);            // k = q + 8 p + 64 s
+                z[q + 8 * (ph + 4) + 64 * sI] = make_float2(r1[sI].x, r1[sI].y);
+            }
+        }
+        __syncwarp();
         if (lane == 0) z[kHalf] = z[0];
         __syncwarp();
         // 4. real-FFT post-processing -> power spectrum P[k], k = 0..256  (kaldi.py:616-618)
@@ -241,18 +321,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) fbank_kernel(
             float2 zk = z[k], zn = z[kHalf - k];
             float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);    // even part
             float orr = 0.5f * (zk.y + zn.y), oi = -0.5f * (zk.x - zn.x);  // odd part
-            float2 w = __ldg(&g_tab.post[k]);
+            float2 w = s_post[k];
             float xr = er + (orr * w.x - oi * w.y);
             float xi = ei + (orr * w.y + oi * w.x);
             pw[k] = xr * xr + xi * xi;
         }
         __syncwarp();
         // 5. mel filterbank (sparse triangles), log floor, store  (kaldi.py:630-633)
-        for (int m = lane; m < kMel; m += 32) {
-            const int st = __ldg(&g_tab.mel_start[m]), ln = __ldg(&g_tab.mel_len[m]), of = __ldg(&g_tab.mel_off[m]);
-            float e = 0.f;
-            for (int k = 0; k < ln; ++k) e = fmaf(pw[st + k], __ldg(&g_tab.mel_w[of + k]), e);
-            out[m] = logf(fmaxf(e, 1.1920928955078125e-07f));
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int m = lane + 32 * r;
+            if (m < kMel) {
+                float e = 0.f;
+                for (int k = 0; k < mln[r]; ++k) e = fmaf(pw[mst[r] + k], s_melw[mof[r] + k], e);
+                out[m] = logf(fmaxf(e, 1.1920928955078125e-07f));
+            }
         }
         __syncwarp();
     }

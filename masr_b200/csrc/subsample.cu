@@ -12,10 +12,13 @@
 
 namespace masr {
 
-// One CTA per output row (b, t): 8 warps take the frequency positions f = warp, warp+8, ...; a lane owns 8 consecutive
-// output channels (weights in registers), so the 9 window values of a position are 9 shared-memory broadcasts for 72 FMAs
-// and the results leave as 128-bit stores (one per fp16 half, or two for fp32).  The first version (thread per channel,
-// 16-bit scalar stores, 9 shared loads per output) was instruction-bound at 75 % issue utilisation (ncu, r01).
+// One CTA per CONV1_TR consecutive output rows of one utterance: 8 warps take the (row, frequency) positions round-robin;
+// a lane owns 8 consecutive output channels (72 weights in registers, loaded once per CTA and amortised over
+// CONV1_TR x W1 positions), so the 9 window values of a position are 9 shared-memory broadcasts for 72 FMAs and the
+// results leave as 128-bit stores (one per fp16 half, or two for fp32).  The first version (thread per channel, 16-bit
+// scalar stores, 9 shared loads per output) was instruction-bound at 75 % issue utilisation (ncu, r01).
+constexpr int CONV1_TR = 4;
+
 __global__ void __launch_bounds__(256) conv1_cmvn_relu_kernel(const float* __restrict__ feats,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ istd,
@@ -23,11 +26,13 @@ __global__ void __launch_bounds__(256) conv1_cmvn_relu_kernel(const float* __res
                                                               float* __restrict__ out, __half* __restrict__ ph,
                                                               __half* __restrict__ pl, int Fmax, int idim, int F1max,
                                                               int W1, int C) {
-    extern __shared__ float s_in[];            // [3][idim] normalised input rows
-    const int b = blockIdx.y, t = blockIdx.x;
-    for (int i = threadIdx.x; i < 3 * idim; i += blockDim.x) {
+    extern __shared__ float s_in[];            // [2*CONV1_TR + 1][idim] normalised input rows
+    const int b = blockIdx.y, t0 = blockIdx.x * CONV1_TR;
+    const int nt = min(CONV1_TR, F1max - t0);  // output rows of this CTA
+    const int nrows = 2 * nt + 1;
+    for (int i = threadIdx.x; i < nrows * idim; i += blockDim.x) {
         int r = i / idim, c = i - r * idim;
-        float v = __ldg(feats + ((int64_t)b * Fmax + 2 * t + r) * idim + c);
+        float v = __ldg(feats + ((int64_t)b * Fmax + 2 * t0 + r) * idim + c);
         if (mean) v = (v - __ldg(mean + c)) * __ldg(istd + c);
         s_in[i] = v;
     }
@@ -42,12 +47,13 @@ __global__ void __launch_bounds__(256) conv1_cmvn_relu_kernel(const float* __res
 #pragma unroll
             for (int k = 0; k < 9; ++k) w[j][k] = __ldg(w1 + (co + j) * 9 + k);
         }
-        for (int f = warp; f < W1; f += 8) {
+        for (int pos = warp; pos < nt * W1; pos += 8) {
+            const int tl = pos / W1, f = pos - tl * W1, t = t0 + tl;
             float x[9];
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) x[kh * 3 + kw] = s_in[kh * idim + 2 * f + kw];
+                for (int kw = 0; kw < 3; ++kw) x[kh * 3 + kw] = s_in[(2 * tl + kh) * idim + 2 * f + kw];
             float acc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -90,7 +96,7 @@ extern "C" int masr_conv1_cmvn_relu_f32(const float* feats, const float* mean, c
     MASR_REQUIRE((mean == nullptr) == (istd == nullptr), "masr_conv1_cmvn_relu_f32: mean/istd must both be set or both null");
     MASR_REQUIRE(2 * (F1max - 1) + 2 < Fmax && 2 * (W1 - 1) + 2 < idim, "masr_conv1_cmvn_relu_f32: window exceeds input");
     MASR_REQUIRE(C % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "masr_conv1_cmvn_relu_f32: C must be a multiple of 8, out 16-byte aligned");
-    conv1_cmvn_relu_kernel<<<dim3(F1max, B), 256, 3 * idim * sizeof(float), (cudaStream_t)stream>>>(
+    conv1_cmvn_relu_kernel<<<dim3((F1max + CONV1_TR - 1) / CONV1_TR, B), 256, (2 * CONV1_TR + 1) * idim * sizeof(float), (cudaStream_t)stream>>>(
         feats, mean, istd, w1, b1, out, nullptr, nullptr, Fmax, idim, F1max, W1, C);
     return check_launch("conv1_cmvn_relu_kernel");
 }
@@ -106,7 +112,7 @@ extern "C" int masr_conv1_cmvn_relu_planes_f16(const float* feats, const float* 
     MASR_REQUIRE(2 * (F1max - 1) + 2 < Fmax && 2 * (W1 - 1) + 2 < idim && W1 <= 40, "masr_conv1_cmvn_relu_planes_f16: bad geometry");
     MASR_REQUIRE(C % 8 == 0 && ((reinterpret_cast<uintptr_t>(planes_h) | reinterpret_cast<uintptr_t>(planes_l)) & 15) == 0,
                  "masr_conv1_cmvn_relu_planes_f16: C must be a multiple of 8, planes 16-byte aligned");
-    conv1_cmvn_relu_kernel<<<dim3(F1max, B), 256, 3 * idim * sizeof(float), (cudaStream_t)stream>>>(
+    conv1_cmvn_relu_kernel<<<dim3((F1max + CONV1_TR - 1) / CONV1_TR, B), 256, (2 * CONV1_TR + 1) * idim * sizeof(float), (cudaStream_t)stream>>>(
         feats, mean, istd, w1, b1, nullptr, (__half*)planes_h, (__half*)planes_l, Fmax, idim, F1max, W1, C);
     return check_launch("conv1_cmvn_relu_kernel<planes>");
 }

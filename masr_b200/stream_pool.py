@@ -511,7 +511,14 @@ def make_pool(eng, n_slots: int, max_frames: int = 3000):
 
 
 class StreamPool:
-    """`predict_stream` for many streams at once (same per-stream results as one ``MASRPredictor`` per stream)."""
+    """`predict_stream` for many streams at once (same per-stream results as one ``MASRPredictor`` per stream).
+
+    Host work per push is O(slots) integer bookkeeping: the un-consumed feature frames of every slot live in ONE device
+    ring ``[S, RING, 80]`` (appended and windowed with two batched index ops per push / per round instead of per-slot
+    tensor ops), and the greedy history is folded incrementally — the reference re-collapses the whole history on every
+    chunk (ctc_greedy_decoder.py:81-88), which yields the same tokens and the same left-to-right float32 score sum."""
+
+    RING = 1024                    # feature frames kept per slot (un-consumed frames never exceed one push + one window)
 
     def __init__(self, eng: ConformerEngine, vocab: Sequence[str], n_slots: int, use_db_normalization: bool = True,
                  target_db: float = -20.0, max_frames: int = 3000):
@@ -519,19 +526,35 @@ class StreamPool:
         self.pool = make_pool(eng, n_slots, max_frames)
         self.use_db, self.target_db = use_db_normalization, target_db
         self.remained: List[Optional[np.ndarray]] = [None] * n_slots
-        self.cached: List[Optional[torch.Tensor]] = [None] * n_slots
-        self.hist_ids: List[List[int]] = [[] for _ in range(n_slots)]
-        self.hist_p: List[list] = [[] for _ in range(n_slots)]
+        dev = eng.device
+        # row S*RING is an all-zero frame: the source of window rows beyond a slot's chunk
+        self.ring = torch.zeros(n_slots * self.RING + 1, 80, device=dev, dtype=torch.float32)
+        self.head = [0] * n_slots      # absolute index of the first un-consumed frame
+        self.count = [0] * n_slots     # un-consumed frames in the ring
+        self._reset_hist(range(n_slots))
+
+    def _reset_hist(self, slots):
+        if not hasattr(self, "toks"):
+            self.toks = [[] for _ in range(self.S)]
+            self.prev = [None] * self.S
+            self.acc = [np.float32(0.0)] * self.S
+            self.nprob = [0] * self.S
+        for s in slots:
+            self.toks[s], self.prev[s], self.acc[s], self.nprob[s] = [], None, np.float32(0.0), 0
 
     def reset_stream(self, slot: int):
         self.pool.reset(slot)
-        self.remained[slot], self.cached[slot] = None, None
-        self.hist_ids[slot], self.hist_p[slot] = [], []
+        self.remained[slot] = None
+        self.head[slot], self.count[slot] = 0, 0
+        self._reset_hist([slot])
+
+    def _dev_index(self, idx: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(idx).to(self.eng.device, non_blocking=False)
 
     def push(self, audio: Dict[int, object], is_end: bool = False, channels: int = 1, samp_width: int = 2):
         """audio: slot -> np.ndarray | PCM bytes (one push per slot).  -> slot -> {'text','score'} | None, exactly what
         ``MASRPredictor.predict_stream(chunk, is_end)`` would return for that stream."""
-        eng, S = self.eng, self.S
+        eng, S, R = self.eng, self.S, self.RING
         slots = sorted(audio)
         for s in slots:
             a = audio[s]
@@ -542,47 +565,59 @@ class StreamPool:
         gains = eng.last_gain.cpu().numpy() if self.use_db else np.ones(len(slots), np.float32)
         if np.any(status.cpu().numpy() != 0):
             raise ValueError("无法将段规范化到目标dB，音频增益已经超过max_gain_db (300.0dB)")
+        Fmax = feats.shape[1]
+        src, dst = [], []
         for j, s in enumerate(slots):
             nf = frames[j]
-            xc = feats[j, :nf]
-            self.cached[s] = xc if self.cached[s] is None else torch.cat([self.cached[s], xc], dim=0)
+            if self.count[s] + nf > R:
+                raise AssertionError(f"stream slot {s}: more than {R} un-consumed feature frames")
+            if nf:
+                f = np.arange(nf, dtype=np.int64)
+                src.append(j * Fmax + f)
+                dst.append(s * R + (self.head[s] + self.count[s] + f) % R)
+                self.count[s] += nf
             tail = self.remained[s][FRAME_SHIFT * nf:]
             self.remained[s] = (tail * np.float32(gains[j])).astype(np.float32) if self.use_db else tail
-        pending = {s: chunk_starts(int(self.cached[s].shape[0]), is_end) for s in slots}
-        touched = {s: bool(pending[s]) for s in slots}
+        if src:                                      # append the new frames of every slot to the ring: one gather + one scatter
+            self.ring.index_copy_(0, self._dev_index(np.concatenate(dst)),
+                                  feats.view(-1, 80).index_select(0, self._dev_index(np.concatenate(src))))
+        pending = {s: chunk_starts(self.count[s], is_end) for s in slots}
         ends = {}
         rounds = max((len(v) for v in pending.values()), default=0)
-        batch = torch.zeros(S, CHUNK_FRAMES, 80, device=eng.device, dtype=torch.float32)
+        zero_row = S * R
+        win = np.arange(CHUNK_FRAMES, dtype=np.int64)
         for r in range(rounds):
             nfr = [0] * S
+            idx = np.full((S, CHUNK_FRAMES), zero_row, np.int64)
             for s in slots:
                 if r < len(pending[s]):
                     cur = pending[s][r]
-                    end = min(cur + CHUNK_FRAMES, int(self.cached[s].shape[0]))
-                    batch[s, :end - cur].copy_(self.cached[s][cur:end])
-                    nfr[s] = end - cur
+                    end = min(cur + CHUNK_FRAMES, self.count[s])
+                    n = end - cur
+                    idx[s, :n] = s * R + (self.head[s] + cur + win[:n]) % R
+                    nfr[s] = n
                     ends[s] = end
+            batch = self.ring.index_select(0, self._dev_index(idx.reshape(-1))).view(S, CHUNK_FRAMES, 80)
             ids, maxp, tout = self.pool.step(batch, nfr)
             ids_h, mp_h = ids.cpu().numpy(), maxp.cpu().numpy()
             for s in slots:
+                prev, acc, toks = self.prev[s], self.acc[s], self.toks[s]
                 for t in range(tout[s]):
                     i = int(ids_h[s, t])
-                    self.hist_ids[s].append(i)
                     if i != 0:
-                        self.hist_p[s].append(mp_h[s, t])
+                        acc = np.float32(acc + mp_h[s, t])
+                        self.nprob[s] += 1
+                        if i != prev:
+                            toks.append(i)
+                    prev = i
+                self.prev[s], self.acc[s] = prev, acc
         out = {}
         for s in slots:
-            if not touched[s]:
+            if not pending[s]:
                 out[s] = None
                 continue
-            self.cached[s] = self.cached[s][ends[s] - CACHED_FEATURE_NUM:]
-            toks, prev = [], None
-            for i in self.hist_ids[s]:
-                if i != prev and i != 0:
-                    toks.append(i)
-                prev = i
-            acc = np.float32(0.0)
-            for p in self.hist_p[s]:
-                acc = np.float32(acc + p)
-            out[s] = {"text": ids_to_text(toks, self.vocab), "score": greedy_score(acc, len(self.hist_p[s]))}
+            consumed = ends[s] - CACHED_FEATURE_NUM              # predict.py:330: keep the last 3 frames of the window
+            self.head[s] = (self.head[s] + consumed) % R
+            self.count[s] -= consumed
+            out[s] = {"text": ids_to_text(self.toks[s], self.vocab), "score": greedy_score(self.acc[s], self.nprob[s])}
         return out
