@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(128) relpos_attention_mma_kernel(AttnMmaParams
     __half* stage0 = sQl + MQ * KC_STRIDE;
 
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MQ;
+    pdl_wait();                                 // programmatic dependent launch: the producer grid has completed
+    pdl_launch_dependents();
     const int qlen = p.q_lens[b], klen = p.k_lens[b];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -323,6 +325,6 @@ extern "C" int masr_relpos_attention_tc(const float* Q, int64_t ldq, int64_t q_b
                     (const __half*)Ph, (const __half*)Pl, ldp, pos_u, pos_v, O, (__half*)Oh, (__half*)Ol, ldo, o_bstride, q_lens,
                     k_lens, 1.4426950408889634f / sqrtf((float)d_k), max_q};
     dim3 grid((max_q + MQ - 1) / MQ, H, B);
-    relpos_attention_mma_kernel<<<grid, 128, kAttnMmaSmem, (cudaStream_t)stream>>>(p);
+    launch_pdl(relpos_attention_mma_kernel, grid, dim3(128), kAttnMmaSmem, (cudaStream_t)stream, p);
     return check_launch("relpos_attention_mma_kernel");
 }

@@ -65,6 +65,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
 __device__ __forceinline__ float fast_silu(float x) { return x * fast_sigmoid(x); }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// The device step is a chain of ~180 short kernels.  Launched with programmaticStreamSerialization, a kernel may start
+// (and run its prologue: barrier init, TMEM allocation, table loads into registers) while its predecessor drains; it
+// blocks in pdl_wait() until the predecessor grid has completed and its memory is visible, BEFORE its first global access.
+// Kernels launched without the attribute see a no-op.  MASR_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // 128-bit streaming global accesses (guide: Guideline 13).
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

@@ -41,10 +41,13 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_silu_kernel(const flo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int t0 = (blockIdx.x * DW_WARPS + warp) * DW_TW;   // first output frame of this warp
+    // (weights are constants of the model, not outputs of the producer kernel: staged before the dependency wait)
     for (int idx = threadIdx.x; idx < KS * C; idx += DW_WARPS * 32) {
         const int k = idx / C, c = idx - k * C;              // reference layout [C, 1, k]; conflict-free shared stores
         s_w[k][c] = __ldg(w + c * KS + k);
     }
+    pdl_wait();                                              // programmatic dependent launch: the producer grid has completed
+    pdl_launch_dependents();
     __syncthreads();
     if (t0 >= out_rows) return;                              // warp-uniform (after the only barrier)
     const int in_len = in_lens[b];
@@ -151,8 +154,8 @@ extern "C" int masr_dwconv_ln_silu_strided_f32(const float* g, int64_t ldg, int6
     dim3 grid((out_rows + TT - 1) / TT, B);
     cudaStream_t st = (cudaStream_t)stream;
 #define MASR_DW_LAUNCH(KS, S)                                                                                       \
-    dwconv_ln_silu_kernel<KS, S, false><<<grid, DW_WARPS * 32, 0, st>>>(g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
-                                                           (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps)
+    launch_pdl(dwconv_ln_silu_kernel<KS, S, false>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
+               (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps)
     MASR_REQUIRE(stride == 1 || stride == 2, "masr_dwconv_ln_silu: stride %d unsupported (1/2)", stride);
     if (stride == 2) {
         MASR_REQUIRE(kernel_size == 15, "masr_dwconv_ln_silu: stride 2 is built for kernel size 15 only");
@@ -186,11 +189,11 @@ extern "C" int masr_dwconv_bn_silu_f32(const float* g, int64_t ldg, int64_t g_bs
     cudaStream_t st = (cudaStream_t)stream;
     switch (kernel_size) {
         case 15:
-            dwconv_ln_silu_kernel<15, 1, true><<<grid, DW_WARPS * 32, 0, st>>>(g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
+            launch_pdl(dwconv_ln_silu_kernel<15, 1, true>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
                 (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, 0.f);
             break;
         case 31:
-            dwconv_ln_silu_kernel<31, 1, true><<<grid, DW_WARPS * 32, 0, st>>>(g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
+            launch_pdl(dwconv_ln_silu_kernel<31, 1, true>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
                 (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, 0.f);
             break;
         default:

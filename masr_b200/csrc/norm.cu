@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ ada_bias = nullptr) {
     static_assert(D % 128 == 0, "D must be a multiple of 128");
     constexpr int V = D / 128;                 // float4 per lane
+    pdl_wait();                                // programmatic dependent launch: the producer grid has completed
+    pdl_launch_dependents();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -83,6 +85,8 @@ __global__ void __launch_bounds__(256) layernorm2_kernel(const float* __restrict
                                                          __half* __restrict__ yl, int64_t ldy, int M, float eps) {
     static_assert(D % 128 == 0, "D must be a multiple of 128");
     constexpr int V = D / 128;
+    pdl_wait();
+    pdl_launch_dependents();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -147,8 +151,8 @@ extern "C" int masr_layernorm2_split_f16(const float* x, int64_t ldx, const floa
     MASR_REQUIRE(x && gamma1 && beta1 && y1 && gamma2 && beta2 && yh && yl, "masr_layernorm2_split_f16: null pointer");
     MASR_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "masr_layernorm2_split_f16: leading dimensions must be multiples of 4");
     MASR_REQUIRE(D == 256, "masr_layernorm2_split_f16: unsupported width D=%d (256)", D);
-    layernorm2_kernel<256><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, ldx, gamma1, beta1, y1, gamma2, beta2, y2,
-                                                                          (__half*)yh, (__half*)yl, ldy, M, eps);
+    launch_pdl(layernorm2_kernel<256>, dim3((M + 7) / 8), dim3(256), 0, (cudaStream_t)stream, x, ldx, gamma1, beta1, y1, gamma2,
+               beta2, y2, (__half*)yh, (__half*)yl, ldy, M, eps);
     return check_launch("layernorm2_kernel");
 }
 
@@ -160,10 +164,10 @@ extern "C" int masr_layernorm_f32(const float* x, int64_t ldx, const float* gamm
     dim3 grid((M + 7) / 8);
     cudaStream_t st = (cudaStream_t)stream;
     switch (D) {
-        case 256: layernorm_kernel<256, false><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, y, nullptr, nullptr, ldy, M, eps); break;
-        case 512: layernorm_kernel<512, false><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, y, nullptr, nullptr, ldy, M, eps); break;
-        case 1024: layernorm_kernel<1024, false><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, y, nullptr, nullptr, ldy, M, eps); break;
-        case 2048: layernorm_kernel<2048, false><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, y, nullptr, nullptr, ldy, M, eps); break;
+        case 256: launch_pdl(layernorm_kernel<256, false>, grid, dim3(256), 0, st, x, ldx, gamma, beta, y, nullptr, nullptr, ldy, M, eps, (const float*)nullptr, (const float*)nullptr); break;
+        case 512: launch_pdl(layernorm_kernel<512, false>, grid, dim3(256), 0, st, x, ldx, gamma, beta, y, nullptr, nullptr, ldy, M, eps, (const float*)nullptr, (const float*)nullptr); break;
+        case 1024: launch_pdl(layernorm_kernel<1024, false>, grid, dim3(256), 0, st, x, ldx, gamma, beta, y, nullptr, nullptr, ldy, M, eps, (const float*)nullptr, (const float*)nullptr); break;
+        case 2048: launch_pdl(layernorm_kernel<2048, false>, grid, dim3(256), 0, st, x, ldx, gamma, beta, y, nullptr, nullptr, ldy, M, eps, (const float*)nullptr, (const float*)nullptr); break;
         default:
             set_last_error("masr_layernorm_f32: unsupported width D=%d (256/512/1024/2048)", D);
             return MASR_ERR_INVALID_ARGUMENT;
@@ -180,9 +184,9 @@ extern "C" int masr_layernorm_split_f16(const float* x, int64_t ldx, const float
     dim3 grid((M + 7) / 8);
     cudaStream_t st = (cudaStream_t)stream;
     switch (D) {
-        case 256: layernorm_kernel<256, true><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, nullptr, (__half*)yh, (__half*)yl, ldy, M, eps); break;
-        case 1024: layernorm_kernel<1024, true><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, nullptr, (__half*)yh, (__half*)yl, ldy, M, eps); break;
-        case 2048: layernorm_kernel<2048, true><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, nullptr, (__half*)yh, (__half*)yl, ldy, M, eps); break;
+        case 256: launch_pdl(layernorm_kernel<256, true>, grid, dim3(256), 0, st, x, ldx, gamma, beta, nullptr, (__half*)yh, (__half*)yl, ldy, M, eps, (const float*)nullptr, (const float*)nullptr); break;
+        case 1024: launch_pdl(layernorm_kernel<1024, true>, grid, dim3(256), 0, st, x, ldx, gamma, beta, nullptr, (__half*)yh, (__half*)yl, ldy, M, eps, (const float*)nullptr, (const float*)nullptr); break;
+        case 2048: launch_pdl(layernorm_kernel<2048, true>, grid, dim3(256), 0, st, x, ldx, gamma, beta, nullptr, (__half*)yh, (__half*)yl, ldy, M, eps, (const float*)nullptr, (const float*)nullptr); break;
         default:
             set_last_error("masr_layernorm_split_f16: unsupported width D=%d (256/1024/2048)", D);
             return MASR_ERR_INVALID_ARGUMENT;
@@ -198,7 +202,7 @@ extern "C" int masr_layernorm_ada_split_f16(const float* x, int64_t ldx, const f
     MASR_REQUIRE(x && gamma && beta && yh && yl, "masr_layernorm_ada_split_f16: null pointer");
     MASR_REQUIRE((ada_scale == nullptr) == (ada_bias == nullptr), "masr_layernorm_ada_split_f16: ada scale/bias come as a pair");
     MASR_REQUIRE(D == 256, "masr_layernorm_ada_split_f16: D=%d unsupported (256)", D);
-    layernorm_kernel<256, true><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, ldx, gamma, beta, y, (__half*)yh, (__half*)yl,
+    launch_pdl(layernorm_kernel<256, true>, dim3((M + 7) / 8), dim3(256), 0, (cudaStream_t)stream, x, ldx, gamma, beta, y, (__half*)yh, (__half*)yl,
                                                                               ldy, M, eps, ada_scale, ada_bias);
     return check_launch("layernorm_kernel<ada,split>");
 }

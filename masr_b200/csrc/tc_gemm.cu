@@ -401,6 +401,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: everything above (barriers, TMEM allocation, descriptor prefetch) overlapped the
+    // producer kernel's tail; no global memory has been touched yet
+    pdl_wait();
+    pdl_launch_dependents();
 
     // tile -> coordinates
     auto decode = [&](int tile, int& n0, int& m0, int& t0, int& b) {
@@ -722,8 +726,8 @@ extern "C" int masr_conv2_tc_f16x2(const void* c1h, const void* c1l, const void*
     const int tiles_n = (C + TBN - 1) / TBN, tiles_t = (T2 + CONV_TR - 1) / CONV_TR;
     const int num_tiles = tiles_n * tiles_t * B;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    if (p.flags & 4) tc_gemm_kernel<true, 16><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t);
-    else tc_gemm_kernel<true, 8><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, tiles_t);
+    if (p.flags & 4) launch_pdl(tc_gemm_kernel<true, 16>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, tiles_t);
+    else launch_pdl(tc_gemm_kernel<true, 8>, dim3(grid), dim3(tc_threads(8)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, tiles_t);
     return check_launch("tc_gemm_kernel<conv>");
 }
 
@@ -762,7 +766,7 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = tiles_n * tiles_m;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    if (p.flags & 4) tc_gemm_kernel<false, 16><<<grid, tc_threads(16), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1);
-    else tc_gemm_kernel<false, 8><<<grid, tc_threads(8), kTcSmem, (cudaStream_t)stream>>>(maps, p, num_tiles, tiles_n, 1);
+    if (p.flags & 4) launch_pdl(tc_gemm_kernel<false, 16>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
+    else launch_pdl(tc_gemm_kernel<false, 8>, dim3(grid), dim3(tc_threads(8)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
     return check_launch("tc_gemm_kernel");
 }

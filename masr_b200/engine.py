@@ -535,12 +535,14 @@ class ConformerEngine:
         return g
 
     # ---- pipelined batches: host staging + H2D of batch k+1 overlap the device step of batch k ---------------------
-    def transcribe_pipelined(self, batches, use_db_normalization: bool = True, target_db: float = -20.0):
+    def transcribe_pipelined(self, batches, use_db_normalization: bool = True, target_db: float = -20.0, device_hook=None):
         """Generator over ``batches`` (an iterable of lists of float32 waveforms) yielding one ``GreedyResult`` per batch,
         in order, each identical to ``transcribe(batch)``.  Two static input sets + two pinned staging buffers: while the
         CUDA graph of batch k runs on the compute stream, batch k+1 is packed into pinned memory by the native stager and
         copied H2D on a separate copy stream; the packed outputs of batch k come back in one D2H copy.  Results lag the
-        input by one batch."""
+        input by one batch.  ``device_hook(out_pack)`` (optional) is called right after each device step is enqueued, with the
+        packed int32 output tensor still on the device — the place to enqueue the cross-rank token gather (NCCL) of a sharded
+        deployment on the same stream."""
         dev = self.device
         comp = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None:
@@ -609,6 +611,8 @@ class ConformerEngine:
                 g["graph"].replay()
                 self.launches += g["launches"]
                 pack = g["ws"]["out_pack"]
+                if device_hook is not None:
+                    device_hook(pack)
                 if P["out"] is None or P["out"].numel() < pack.numel():
                     P["out"] = torch.empty(max(4096, 2 * pack.numel()), dtype=torch.int32, pin_memory=True)
                 P["out"][:pack.numel()].copy_(pack, non_blocking=True)

@@ -171,11 +171,11 @@ class MASRPredictor:
         vocab = self._text_featurizer.vocab_list
         return [{'text': ids_to_text(t, vocab), 'score': s} for t, s in zip(res.tokens, res.scores)]
 
-    def predict_batches(self, batches, sample_rate=16000):
+    def predict_batches(self, batches, sample_rate=16000, device_hook=None):
         """Additive: a stream of batches (iterable of lists of utterances) -> one list of ``{'text','score'}`` per batch, in
         order; element i of batch k equals ``predict(batches[k][i])``.  Host staging and the H2D copy of batch k+1 overlap
         the GPU pass of batch k (``ConformerEngine.transcribe_pipelined``), so the results lag the input by one batch.
-        Greedy decoding only."""
+        Greedy decoding only.  ``device_hook``: see ``transcribe_pipelined`` (cross-rank gather of a sharded deployment)."""
         if self._beam_conf is not None:
             for b in batches:
                 yield self.predict_batch(b, sample_rate)
@@ -190,7 +190,7 @@ class MASRPredictor:
                     self._check_rate(sr)
                     waves.append(s)
                 yield waves
-        for res in self.predictor.transcribe_pipelined(loaded(), self._use_db, self._target_db):
+        for res in self.predictor.transcribe_pipelined(loaded(), self._use_db, self._target_db, device_hook=device_hook):
             self._raise_status(res.status)
             yield [{'text': ids_to_text(t, vocab), 'score': s} for t, s in zip(res.tokens, res.scores)]
 
