@@ -184,6 +184,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     _b.build()

@@ -919,16 +919,16 @@ class EfficientConformerEngine(ConformerEngine):
     def final_len(self, t: int) -> int:
         return (t + 1) // 2
 
-    def new_stream(self, max_frames: int = 3000):
+    def new_stream(self, max_frames: int = 3000, keep_probs: bool = False):
         """Streaming state of one utterance (att/cnn caches + offset): a one-slot stream pool."""
         from .stream_pool import EfficientConformerStreamPool, PoolStream
-        return PoolStream(EfficientConformerStreamPool(self, 1, max_frames))
+        return PoolStream(EfficientConformerStreamPool(self, 1, max_frames, keep_probs=keep_probs))
 
     def encode_chunk(self, feats_chunk, st, required_cache_size: int = -1, want_probs: bool = False):
         """``EfficientConformerModel.get_encoder_out_chunk`` for one stream (encoder.py:267-392): feats_chunk [n<=67, 80] on
         device -> (ids, max-prob) device tensors, one per 80 ms output frame."""
-        if want_probs:
-            raise NotImplementedError("posteriors of the chunk path are not exposed for this model")
+        if want_probs and st.pool.probs is None:
+            raise ValueError("create the stream with new_stream(keep_probs=True) to get the chunk posteriors")
         return st.encode_chunk(feats_chunk, required_cache_size)
 
     def _encode_tc(self, feats, ws, tl, tlens, B, Fmax, F1, T, M):

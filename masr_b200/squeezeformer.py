@@ -179,16 +179,16 @@ class SqueezeformerEngine(ConformerEngine):
             t[i, "pw1"], t[i, "pw2"] = self._split(L.pw1), self._split(L.pw2)
         torch.cuda.synchronize(self.device)
 
-    def new_stream(self, max_frames: int = 3000):
+    def new_stream(self, max_frames: int = 3000, keep_probs: bool = False):
         """Streaming state of one utterance (``InferencePredictor`` att/cnn caches + offset): a one-slot stream pool."""
         from .stream_pool import PoolStream, SqueezeformerStreamPool
-        return PoolStream(SqueezeformerStreamPool(self, 1, max_frames))
+        return PoolStream(SqueezeformerStreamPool(self, 1, max_frames, keep_probs=keep_probs))
 
     def encode_chunk(self, feats_chunk, st, required_cache_size: int = -1, want_probs: bool = False):
         """``SqueezeformerModel.get_encoder_out_chunk`` for one stream (encoder.py:240-361): feats_chunk [n<=67, 80] on device
         -> (ids, max-prob) device tensors of length ((n-1)//2-1)//2."""
-        if want_probs:
-            raise NotImplementedError("posteriors of the chunk path are not exposed for this model")
+        if want_probs and st.pool.probs is None:
+            raise ValueError("create the stream with new_stream(keep_probs=True) to get the chunk posteriors")
         return st.encode_chunk(feats_chunk, required_cache_size)
 
     def _ln_ada(self, x, gb, y, ada, yp, M):

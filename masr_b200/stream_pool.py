@@ -1,4 +1,4 @@
-"""Many live streams on one GPU: batched chunk decoding for the streaming Conformer.
+"""Many live streams on one GPU: batched chunk decoding for the streaming Conformer, Squeezeformer and EfficientConformer.
 
 The reference's streaming API is one stream per ``MASRPredictor`` (predict.py:237-343; ``forward_chunk`` asserts
 batch 1, conformer/encoder.py:378) and `infer_server.py` effectively serves one stream at a time.  BASELINE.json
@@ -39,8 +39,11 @@ class _PoolBase:
     QLEN, KLEN, BASE, QLEN2, KLEN2, BASE2 = range(6)
     OUT_ROWS = CHUNK_OUT          # output frames per slot and chunk (8 for the EfficientConformer)
 
-    def _init_common(self, eng, n_slots: int, use_graph: bool):
+    def _init_common(self, eng, n_slots: int, use_graph: bool, keep_probs: bool = False):
         self.eng, self.S = eng, n_slots
+        # keep_probs: also write the CTC posteriors of every output frame ([S * OUT_ROWS, V], `self.probs`) — the
+        # `InferencePredictor.predict_chunk_conformer` seam (inference_predictor.py:80-94) returns them
+        self.probs = (torch.zeros(n_slots * self.OUT_ROWS, eng.V, device=eng.device, dtype=torch.float32) if keep_probs else None)
         dev = eng.device
         self.meta = torch.zeros(6, n_slots, device=dev, dtype=torch.int32)
         self.meta_host = torch.zeros(6, n_slots, dtype=torch.int32, pin_memory=True)
@@ -128,12 +131,12 @@ class ConformerStreamPool(_PoolBase):
 
     SHORT_ONCE = False            # every block runs at the full frame rate: short chunks may be followed by more chunks
 
-    def __init__(self, eng: ConformerEngine, n_slots: int, max_frames: int = 3000, use_graph: bool = True):
+    def __init__(self, eng: ConformerEngine, n_slots: int, max_frames: int = 3000, use_graph: bool = True, keep_probs: bool = False):
         if not eng.causal:
             raise Exception("chunk decoding needs a streaming (causal) model")
         if eng.gemm_path != "tc":
             raise Exception("the stream pool runs on the tensor-core path")
-        self._init_common(eng, n_slots, use_graph)
+        self._init_common(eng, n_slots, use_graph, keep_probs)
         self.cap = max_frames
         dev, d, w = eng.device, eng.d, eng.w
         f16, f32 = torch.float16, torch.float32
@@ -159,7 +162,6 @@ class ConformerStreamPool(_PoolBase):
             "g": torch.empty(S * (self.lorder + C), d, device=dev, dtype=f32),
             "logits": torch.empty(M, eng.Vpad, device=dev, dtype=f32),
             "ids": torch.empty(M, device=dev, dtype=torch.int32), "maxp": torch.empty(M, device=dev, dtype=f32),
-            "qlen": torch.zeros(S, device=dev, dtype=torch.int32), "klen": torch.zeros(S, device=dev, dtype=torch.int32),
             "clen": torch.full((S,), self.lorder + C, device=dev, dtype=torch.int32),
         }
 
@@ -213,7 +215,7 @@ class ConformerStreamPool(_PoolBase):
             eng._ln(x, L.ln_final, x, M)
         eng._ln_split(x, w.after_norm, t0p, M)
         eng._tc(t0p, d, tw["ctc"], w.ctc_b, M, eng.V, d, C=b["logits"], ldc=eng.Vpad)
-        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
+        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M, eng.V, _p(b["ids"]), _p(b["maxp"]), _p(self.probs), eng.V)
 
 
 class SqueezeformerStreamPool(_PoolBase):
@@ -228,10 +230,10 @@ class SqueezeformerStreamPool(_PoolBase):
 
     SHORT_ONCE = True
 
-    def __init__(self, eng, n_slots: int, max_frames: int = 3000, use_graph: bool = True):
+    def __init__(self, eng, n_slots: int, max_frames: int = 3000, use_graph: bool = True, keep_probs: bool = False):
         if not eng.causal:
             raise Exception("chunk decoding needs a streaming (causal) model")
-        self._init_common(eng, n_slots, use_graph)
+        self._init_common(eng, n_slots, use_graph, keep_probs)
         self.cap = (max_frames + 15) // 16 * 16
         self.cap2 = self.cap // 2
         dev, d, w = eng.device, eng.d, eng.w
@@ -263,8 +265,6 @@ class SqueezeformerStreamPool(_PoolBase):
             "g": torch.empty(S * LC, d, device=dev, dtype=f32),
             "logits": torch.empty(M, eng.Vpad, device=dev, dtype=f32),
             "ids": torch.empty(M, device=dev, dtype=torch.int32), "maxp": torch.empty(M, device=dev, dtype=f32),
-            "qlen": torch.zeros(S, device=dev, dtype=torch.int32), "klen": torch.zeros(S, device=dev, dtype=torch.int32),
-            "qlen2": torch.zeros(S, device=dev, dtype=torch.int32), "klen2": torch.zeros(S, device=dev, dtype=torch.int32),
             "clen": torch.full((S,), self.lorder + C, device=dev, dtype=torch.int32),
             "clen2": torch.full((S,), self.lorder + C2, device=dev, dtype=torch.int32),
         }
@@ -339,7 +339,7 @@ class SqueezeformerStreamPool(_PoolBase):
             nxt = w.layers[i + 1].att_ada if (i + 1 < nl and i + 1 not in (eng.REDUCE, eng.RECOVER)) else None
             eng._ln_ada(y, L.ln4, x, nxt, t0p, Mi)       # last block: pair(x) feeds the CTC head
         eng._tc(t0p, d, tw["ctc"], w.ctc_b, M, eng.V, d, C=b["logits"], ldc=eng.Vpad)
-        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
+        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M, eng.V, _p(b["ids"]), _p(b["maxp"]), _p(self.probs), eng.V)
 
 
 class EfficientConformerStreamPool(_PoolBase):
@@ -356,10 +356,10 @@ class EfficientConformerStreamPool(_PoolBase):
     SHORT_ONCE = True
     OUT_ROWS = CHUNK_OUT // 2
 
-    def __init__(self, eng, n_slots: int, max_frames: int = 3000, use_graph: bool = True):
+    def __init__(self, eng, n_slots: int, max_frames: int = 3000, use_graph: bool = True, keep_probs: bool = False):
         if not eng.causal:
             raise Exception("chunk decoding needs a streaming (causal) model")
-        self._init_common(eng, n_slots, use_graph)
+        self._init_common(eng, n_slots, use_graph, keep_probs)
         self.cap = (max_frames + 15) // 16 * 16
         self.cap2 = self.cap // 2
         dev, d, w = eng.device, eng.d, eng.w
@@ -391,8 +391,6 @@ class EfficientConformerStreamPool(_PoolBase):
             "g": torch.empty(S * LCmax, d, device=dev, dtype=f32),
             "logits": torch.empty(S * C2, eng.Vpad, device=dev, dtype=f32),
             "ids": torch.empty(S * C2, device=dev, dtype=torch.int32), "maxp": torch.empty(S * C2, device=dev, dtype=f32),
-            "qlen": torch.zeros(S, device=dev, dtype=torch.int32), "klen": torch.zeros(S, device=dev, dtype=torch.int32),
-            "qlen2": torch.zeros(S, device=dev, dtype=torch.int32), "klen2": torch.zeros(S, device=dev, dtype=torch.int32),
             "clen": torch.full((S,), LCmax, device=dev, dtype=torch.int32),
         }
 
@@ -469,7 +467,7 @@ class EfficientConformerStreamPool(_PoolBase):
             eng._ln(x, L.ln_final, x, Mo)
         eng._ln_split(x, w.after_norm, t0p, M2)
         eng._tc(t0p, d, tw["ctc"], w.ctc_b, M2, eng.V, d, C=b["logits"], ldc=eng.Vpad)
-        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M2, eng.V, _p(b["ids"]), _p(b["maxp"]), None, eng.V)
+        eng._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(b["logits"]), eng.Vpad, M2, eng.V, _p(b["ids"]), _p(b["maxp"]), _p(self.probs), eng.V)
 
 
 class PoolStream:
@@ -494,7 +492,8 @@ class PoolStream:
             return None
         self.batch[0, :n].copy_(feats_chunk)
         ids, maxp, tout = self.pool.step(self.batch, [n])
-        return ids[0, :tout[0]], maxp[0, :tout[0]], None
+        probs = None if self.pool.probs is None else self.pool.probs[:tout[0]]
+        return ids[0, :tout[0]], maxp[0, :tout[0]], probs
 
 
 def make_pool(eng, n_slots: int, max_frames: int = 3000):

@@ -110,7 +110,7 @@ def test_gpu_pool_matches_oracle_chunk_by_chunk(weights):
     feats = [ob.featurize(make_audio(k, seed, n)) for k, seed, n in
              [("speech", 40, 16000 * 3 + 2000), ("noise", 41, 16000 * 2 + 9000), ("speech", 42, 16000 * 2)]]
     S = 4
-    pool = SqueezeformerStreamPool(eng, S, max_frames=400)
+    pool = SqueezeformerStreamPool(eng, S, max_frames=400, keep_probs=True)     # + the chunk posteriors (InferencePredictor seam)
     states = [osq.ChunkState() for _ in feats]
     # chunk schedule per slot: list of (cur, end) windows like predict_stream with is_end at the end
     sched = []
@@ -142,6 +142,8 @@ def test_gpu_pool_matches_oracle_chunk_by_chunk(weights):
             assert tout[i] == probs.shape[0]
             assert np.array_equal(ids_h[i, :tout[i]], probs.argmax(1)), (r, i)
             assert np.abs(mp_h[i, :tout[i]] - probs.max(1)).max() < 5e-5, (r, i)
+            got = pool.probs.view(S, -1, probs.shape[1])[i, :tout[i]].cpu().numpy()
+            assert np.abs(got - probs).max() < 5e-5, (r, i)
     assert saw_short
     # a slot that decoded a short chunk must be reset before it is used again
     with pytest.raises(AssertionError):

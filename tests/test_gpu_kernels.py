@@ -264,3 +264,46 @@ def test_layernorm2_is_two_layernorms(rt):
     assert torch.equal(xin, y1) and torch.equal(o2, y2) and torch.equal(oh, rh) and torch.equal(ol, rl)
     ref = F.layer_norm(F.layer_norm(x.cpu(), (D,), g1.cpu(), b1.cpu()), (D,), g2.cpu(), b2.cpu())
     assert maxdiff(o2, ref) < 2e-5
+
+
+def test_stream_cache_bookkeeping(rt):
+    """masr_stream_append_rows / masr_stream_shift_cache against plain indexing (fp16 pair form and fp32 form)."""
+    g = torch.Generator().manual_seed(3)
+    S, C, cap, d = 5, 16, 64, 256
+    base = torch.tensor([0, 16, 32, 3, 48], dtype=torch.int32)
+    cnt = torch.tensor([16, 0, 5, 16, 1], dtype=torch.int32)
+    src_h = torch.randn(S * C, 3 * d, generator=g).half().to(rt.dev); src_l = torch.randn(S * C, 3 * d, generator=g).half().to(rt.dev)
+    dst_h = torch.zeros(S * cap, 2 * d, dtype=torch.float16, device=rt.dev); dst_l = torch.zeros_like(dst_h)
+    bd, cd = base.to(rt.dev), cnt.to(rt.dev)
+    rt.call("masr_stream_append_rows", P(src_h), P(src_l), 3 * d * 2, d * 2, 2 * d * 2, P(dst_h), P(dst_l), 2 * d * 2, cap, P(bd), P(cd), C, S, rt.st())
+    want_h = torch.zeros_like(dst_h); want_l = torch.zeros_like(dst_l)
+    for s in range(S):
+        for t in range(int(cnt[s])):
+            want_h[s * cap + int(base[s]) + t] = src_h[s * C + t, d:]
+            want_l[s * cap + int(base[s]) + t] = src_l[s * C + t, d:]
+    assert torch.equal(dst_h, want_h) and torch.equal(dst_l, want_l)
+    src32 = torch.randn(S * C, 2 * d, generator=g).to(rt.dev)
+    dst32 = torch.zeros(S * cap, 2 * d, device=rt.dev)
+    rt.call("masr_stream_append_rows", P(src32), None, 2 * d * 4, 0, 2 * d * 4, P(dst32), None, 2 * d * 4, cap, P(bd), P(cd), C, S, rt.st())
+    for s in range(S):
+        n = int(cnt[s])
+        assert torch.equal(dst32[s * cap + int(base[s]): s * cap + int(base[s]) + n], src32[s * C: s * C + n])
+    # slide the conv left context: rows [0, lorder) <- rows [n, n + lorder), overlapping moves included
+    lorder, LC = 14, 30
+    x = torch.randn(S, LC, d, generator=g).to(rt.dev)
+    ref = x.clone()
+    for s in range(S):
+        n = int(cnt[s])
+        if n:
+            ref[s, :lorder] = x[s, n:n + lorder]
+    y = x.clone()
+    rt.call("masr_stream_shift_cache", P(y), None, LC, lorder, d * 4, P(cd), S, rt.st())
+    assert torch.equal(y, ref)
+    xh, xl = x.half(), (x * 3).half()
+    rh, rl = xh.clone(), xl.clone()
+    for s in range(S):
+        n = int(cnt[s])
+        if n:
+            rh[s, :lorder] = xh[s, n:n + lorder]; rl[s, :lorder] = xl[s, n:n + lorder]
+    rt.call("masr_stream_shift_cache", P(xh), P(xl), LC, lorder, d * 2, P(cd), S, rt.st())
+    assert torch.equal(xh, rh) and torch.equal(xl, rl)

@@ -1,5 +1,6 @@
 """Dev tool (run under ncu): a handful of masr_gemm_tc_f16x2 launches on the FFN shapes of the headline step
-(M = 7936): w_1 with MASR_TC_FLAGS=5 and 13, w_2 with 5.  `ncu --set full -k regex:tc_gemm -c 6 ...`."""
+(M = 7936): w_1 once per MASR_TC_FLAGS value in GP_FLAGS (default 5), then w_2.  `ncu --set full -k regex:tc_gemm -c 4 ...`.
+(r01: GP_FLAGS=5,13 compared the plain kernel with the since-removed A-resident variant, profiles/r01_gemm_prof*.)"""
 import os
 import sys
 
@@ -41,6 +42,6 @@ def run(N, K, epi, want_c, want_p, want_r, flags, reps=2):
     torch.cuda.synchronize()
 
 
-for fl in os.environ.get("GP_FLAGS", "5,13").split(","):
+for fl in os.environ.get("GP_FLAGS", "5").split(","):
     run(2048, 256, 1, False, True, False, int(fl))
 run(256, 2048, 5, True, False, True, 5)
