@@ -11,13 +11,15 @@
 // Replaces the same reference call sites as gemm.cu (positionwise.py:37, attention.py:72-74,119,
 // convolution.py:117-118,127, subsampling.py:110, loss/ctc.py:70).
 //
-// Structure (one 128x128 output tile per CTA, 192 threads):
+// Structure (persistent: one CTA per SM walks 128x128 output tiles; 64 + 32*EW threads, EW = 16 epilogue warps by default):
 //   warp 0   TMA producer: 4 boxes per K-block (Ah, Al, Wh, Wl; 64 halves = one 128-byte swizzle row)
-//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs per K-block)
-//   warps 2-5 epilogue: tcgen05.ld 32x32b -> registers -> fused bias/SiLU/ReLU/GLU/scale/residual ->
-//            global (fp32, or the fp16 (h,l) pair the next GEMM consumes)
-//   smem ring of STAGES x 64 KB with full/empty mbarriers; tcgen05.commit releases slots and signals
-//   the epilogue.
+//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (12 MMAs per K-block); main accumulator ping-pong by
+//            256-wide K chunk, correction accumulator ping-pong by tile (512 TMEM columns), so the MMAs of tile i+1
+//            run while the epilogue drains tile i
+//   warps 2.. epilogue: tcgen05.ld 32x32b -> registers -> fused bias/SiLU/ReLU/GLU/scale/residual -> transposed
+//            through shared memory -> row-contiguous 128-bit stores (fp32 and/or the fp16 (h,l) pair the next GEMM consumes)
+//   smem ring of 3 x 64 KB stages with full/empty mbarriers; tcgen05.commit releases slots and signals the epilogue.
+//   Launched with programmatic dependent launch: the prologue overlaps the producer kernel's tail.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <mutex>
