@@ -1,0 +1,123 @@
+"""CPU: the host logic of ``StreamPool.push`` (per-stream sample carry-over with in-place renormalisation, device feature
+ring, 67/64/3 windowing, batched rounds, incremental greedy history) driven by a stand-in engine built from the ORACLE
+(fbank + chunk forward on torch-CPU).  Three interleaved streams — one of them the utterance frozen from the reference's
+``MASRPredictor.predict_stream`` (tests/golden/predictor_golden.json) — must return, push by push, what one
+``predict_stream`` per stream returns.  (The oracle is the stand-in here, i.e. test infrastructure; the product classes
+under test are StreamPool and its ring/windowing logic.)"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_audio, synth_weights
+from masr_b200 import stream_pool as sp, synth
+from masr_b200.engine import subsampled_len
+from masr_b200.predict import CACHED_FEATURE_NUM, DECODING_WINDOW, chunk_starts
+from oracle import conformer as oc, ctc as octc, fbank as ob
+
+
+class OracleEngine:
+    """The two engine entry points StreamPool uses, on the CPU."""
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.last_gain = None
+
+    def fbank(self, waves, use_db=True, target_db=-20.0):
+        feats, frames, gains = [], [], []
+        for w in waves:
+            x, g = ob.normalize_gain(np.asarray(w, np.float32).copy(), target_db) if use_db else (w, np.float32(1))
+            f = ob.kaldi_fbank(ob.to_int16(x))
+            feats.append(f); frames.append(f.shape[0]); gains.append(g)
+        Fmax = max(1, max(frames))
+        out = torch.zeros(len(waves), Fmax, 80)
+        for i, f in enumerate(feats):
+            out[i, :f.shape[0]] = torch.from_numpy(f)
+        self.last_gain = torch.tensor(gains, dtype=torch.float32)
+        return out, frames, torch.zeros(len(waves), dtype=torch.int32)
+
+
+class OraclePool:
+    """``pool.step`` semantics of the CUDA pools (ids / max-prob per slot, valid counts) from the oracle chunk forward."""
+
+    def __init__(self, sd, n_slots):
+        self.sd, self.cfg, self.S = sd, oc.ConformerConfig(), n_slots
+        self.st = [oc.ChunkState() for _ in range(n_slots)]
+
+    def reset(self, slot):
+        self.st[slot] = oc.ChunkState()
+
+    def step(self, feats, nframes):
+        ids = torch.zeros(self.S, 16, dtype=torch.int32)
+        maxp = torch.zeros(self.S, 16)
+        tout = [subsampled_len(int(n)) for n in nframes]
+        for s, n in enumerate(nframes):
+            if tout[s]:
+                with torch.no_grad():
+                    probs = oc.get_encoder_out_chunk(self.sd, self.cfg, feats[s:s + 1, :n], self.st[s], -16)[0]
+                ids[s, :tout[s]] = probs.argmax(1).to(torch.int32)
+                maxp[s, :tout[s]] = probs.max(1).values
+        return ids, maxp, tout
+
+
+def oracle_predict_stream(sd, pcm, push, vocab):
+    st, gs, cfg = oc.ChunkState(), octc.GreedyStream(), oc.ConformerConfig()
+    remained, cached, out = None, None, []
+    for s in range(0, len(pcm), push):
+        is_end = s + push >= len(pcm)
+        new = ob.pcm_bytes_to_float32(pcm[s:s + push].tobytes())
+        remained = new if remained is None else np.concatenate([remained, new])
+        x, _ = ob.normalize_gain(remained.copy())
+        feat = ob.kaldi_fbank(ob.to_int16(x))
+        cached = feat if cached is None else np.concatenate([cached, feat], axis=0)
+        remained = x[160 * feat.shape[0]:]
+        starts = chunk_starts(cached.shape[0], is_end)
+        if not starts:
+            out.append(None)
+            continue
+        res, end = None, None
+        for cur in starts:
+            end = min(cur + DECODING_WINDOW, cached.shape[0])
+            with torch.no_grad():
+                probs = oc.get_encoder_out_chunk(sd, cfg, torch.from_numpy(cached[cur:end])[None], st, -16)[0].numpy()
+            res = gs.push(probs, vocab)
+        cached = cached[end - CACHED_FEATURE_NUM:]
+        out.append({"text": res[1], "score": res[0]})
+    return out
+
+
+def test_stream_pool_host_logic_matches_predict_stream(monkeypatch, predictor_golden):
+    g = predictor_golden
+    sd = synth.to_torch(synth_weights(g["wseed"]))
+    vocab = synth.vocabulary()
+    S = 4
+    monkeypatch.setattr(sp, "make_pool", lambda eng, n, max_frames=3000: OraclePool(sd, n))
+    monkeypatch.setattr(sp.StreamPool, "RING", 256)            # small ring: the wrap-around path is exercised
+    pool = sp.StreamPool(OracleEngine(), vocab, n_slots=S)
+    audios = [make_audio(g["kind"], g["aseed"], g["samples"]), make_audio("noise", 95, 16000 * 2 + 3000), make_audio("speech", 96, 16000 * 4)]
+    pcms = [(np.clip(a, -1, 1) * 32767).astype("<i2") for a in audios]
+    push = g["push"]
+    want = [oracle_predict_stream(sd, p, push, vocab) for p in pcms]
+    for r, w in zip(want[0], g["pushes_pcm"]):                # the stand-in itself reproduces the reference's frozen pushes
+        assert (r is None) == (w is None) and (r is None or (r["text"] == w["text"] and abs(r["score"] - w["score"]) < 1e-3))
+    got = [[] for _ in pcms]
+    npush = [len(range(0, len(p), push)) for p in pcms]
+    for k in range(max(npush)):
+        mid = {i: pcms[i][k * push:(k + 1) * push].tobytes() for i in range(len(pcms)) if k < npush[i] - 1}
+        last = {i: pcms[i][k * push:(k + 1) * push].tobytes() for i in range(len(pcms)) if k == npush[i] - 1}
+        for grp, is_end in ((mid, False), (last, True)):
+            if grp:
+                out = pool.push(grp, is_end=is_end)
+                for i in grp:
+                    got[i].append(out[i])
+    for i in range(len(pcms)):
+        assert len(got[i]) == len(want[i])
+        for r, w in zip(got[i], want[i]):
+            assert (r is None) == (w is None), (i, r, w)
+            if r is not None:
+                assert r["text"] == w["text"], (i, r, w)
+                assert abs(r["score"] - w["score"]) < 1e-4
+    # a slot can be reset and reused
+    pool.reset_stream(1)
+    out = pool.push({1: pcms[1][:push * 3].tobytes()}, is_end=True)
+    ref = oracle_predict_stream(sd, pcms[1][:push * 3], push * 3, vocab)
+    assert out[1]["text"] == ref[-1]["text"]
