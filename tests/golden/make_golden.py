@@ -359,11 +359,52 @@ def gen_predictor_efficient(tmp):
     print("pushes", pushes)
 
 
+DS2_STREAM_CASE = ("ds2_stream_speech_3p75s", 0, "speech", 33, 60000, 8000)  # weight seed, kind, audio seed, samples, push
+
+
+def gen_predictor_deepspeech2(tmp):
+    """The real ``MASRPredictor`` with the streaming (unidirectional) DeepSpeech2, greedy: whole utterance and PCM pushes."""
+    from masr.model_utils.deepspeech2.model import DeepSpeech2Model
+    from masr.predict import MASRPredictor
+    name, wseed, kind, aseed, n, push = DS2_STREAM_CASE
+    cfg = yaml.safe_load(open(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "deepspeech2.yml"), encoding="utf-8"))
+    mi = os.path.join(tmp, f"mean_istd_{wseed}.json")
+    synth.write_mean_istd(mi, wseed)
+    model = DeepSpeech2Model(input_dim=80, vocab_size=V, mean_istd_path=mi, streaming=True,
+                             encoder_conf=cfg["encoder_conf"], decoder_conf=cfg["decoder_conf"])
+    model.load_state_dict(synth.to_torch(synth.deepspeech2_state_dict(wseed, V, streaming=True)), strict=True)
+    mp = os.path.join(tmp, "inference_ds2.pt")
+    torch.jit.save(model.eval().export(), mp)
+    vp = os.path.join(tmp, "vocabulary.txt")
+    synth.write_vocabulary(vp, V)
+    cfg["dataset_conf"]["dataset_vocab"] = vp
+    cfg["dataset_conf"]["mean_istd_path"] = mi
+    cfg["decoder"] = "ctc_greedy"
+    cfg["streaming"] = True
+    np.random.seed(0)
+    pred = MASRPredictor(configs=cfg, model_path=mp, use_gpu=False)
+    x = make_audio(kind, aseed, n)
+    whole = pred.predict(audio_data=x.copy())
+    pcm = (np.clip(x, -1, 1) * 32767).astype("<i2")
+    pushes = []
+    pred.reset_stream()
+    for s in range(0, len(pcm), push):
+        r = pred.predict_stream(audio_data=pcm[s:s + push].tobytes(), is_end=s + push >= len(pcm))
+        pushes.append(None if r is None else {"text": r["text"], "score": r["score"]})
+    pred.reset_stream()
+    data = {"name": name, "wseed": wseed, "kind": kind, "aseed": aseed, "samples": n, "push": push,
+            "whole": whole, "pushes_pcm": pushes}
+    with open(os.path.join(HERE, "predictor_golden_deepspeech2.json"), "w", encoding="utf-8") as f:
+        json.dump(data, f, ensure_ascii=False, indent=1)
+    print("deepspeech2 predictor whole", whole)
+    print("pushes", pushes)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     with tempfile.TemporaryDirectory() as tmp:
         which = sys.argv[1:] or ["fbank", "encoder", "predictor", "efficient", "squeezeformer", "deepspeech2",
-                                  "predictor_squeezeformer", "predictor_efficient"]
+                                  "predictor_squeezeformer", "predictor_efficient", "predictor_deepspeech2"]
         if "deepspeech2" in which:
             gen_deepspeech2(tmp)
         if "squeezeformer" in which:
@@ -378,5 +419,7 @@ if __name__ == "__main__":
             gen_predictor_squeezeformer(tmp)
         if "predictor_efficient" in which:
             gen_predictor_efficient(tmp)
+        if "predictor_deepspeech2" in which:
+            gen_predictor_deepspeech2(tmp)
         if "efficient" in which:
             gen_efficient(tmp)

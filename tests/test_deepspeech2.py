@@ -92,3 +92,53 @@ def test_gpu_engine_matches_oracle_and_golden(streaming, wseed):
             ids, maxp, probs = eng.encode_chunk(fd[cur:cur + 67], st_g, want_probs=True)
             assert np.abs(probs.cpu().numpy() - pm.numpy()).max() < 5e-5
             assert np.array_equal(ids.cpu().numpy(), pm.numpy().argmax(1))
+
+
+def test_oracle_chunk_path_reproduces_reference_predict_stream():
+    """The oracle's chunked forward (LSTM state carried across 67-frame windows) + greedy history reproduces what the
+    reference's real ``MASRPredictor.predict_stream`` returned push by push (tests/golden/predictor_golden_deepspeech2.json,
+    made by make_golden.py)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from masr_b200.predict import CACHED_FEATURE_NUM, DECODING_WINDOW, chunk_starts
+    with open(os.path.join(GOLDEN, "predictor_golden_deepspeech2.json"), encoding="utf-8") as f:
+        g = json.load(f)
+    sd = synth.to_torch(weights(g["wseed"], True))
+    cfg = od.DS2Config(bidirectional=False)
+    vocab = synth.vocabulary()
+    x = make_audio(g["kind"], g["aseed"], g["samples"])
+    with torch.no_grad():
+        probs, _ = od.get_encoder_out(sd, cfg, torch.from_numpy(ob.featurize(x.copy()))[None])
+    score, text, _ = octc.greedy_decode(probs.numpy(), vocab)
+    assert text == g["whole"]["text"] and abs(score - g["whole"]["score"]) < 1e-3
+    pcm = (np.clip(x, -1, 1) * 32767).astype("<i2")
+    push = g["push"]
+    state, gs = None, octc.GreedyStream()
+    remained, cached, got = None, None, []
+    for s in range(0, len(pcm), push):
+        is_end = s + push >= len(pcm)
+        new = ob.pcm_bytes_to_float32(pcm[s:s + push].tobytes())
+        remained = new if remained is None else np.concatenate([remained, new])
+        xn, _ = ob.normalize_gain(remained.copy())
+        feat = ob.kaldi_fbank(ob.to_int16(xn))
+        cached = feat if cached is None else np.concatenate([cached, feat], axis=0)
+        remained = xn[160 * feat.shape[0]:]
+        starts = chunk_starts(cached.shape[0], is_end)
+        if not starts:
+            got.append(None)
+            continue
+        res, end = None, None
+        for cur in starts:
+            end = min(cur + DECODING_WINDOW, cached.shape[0])
+            with torch.no_grad():
+                pr, state = od.get_encoder_out(sd, cfg, torch.from_numpy(cached[cur:end])[None], state)
+            res = gs.push(pr.numpy(), vocab)
+        cached = cached[end - CACHED_FEATURE_NUM:]
+        got.append({"text": res[1], "score": res[0]})
+    assert len(got) == len(g["pushes_pcm"])
+    for r, w in zip(got, g["pushes_pcm"]):
+        assert (r is None) == (w is None)
+        if r is not None:
+            assert r["text"] == w["text"]
+            assert abs(r["score"] - w["score"]) < 1e-3

@@ -67,3 +67,27 @@ def test_beam_search_decoder_config(tmp_path):
     assert abs(out["score"] - score) < 5e-3 * max(1.0, abs(score))
     outs = pred.predict_batch([x.copy(), x[:20000].copy()])
     assert outs[0]["text"] == out["text"]
+
+
+def test_deepspeech2_predict_stream_matches_reference_golden(tmp_path):
+    """The streaming (unidirectional) DeepSpeech2 through ``MASRPredictor.predict_stream`` against the pushes frozen from the
+    reference's real predictor (tests/golden/predictor_golden_deepspeech2.json)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "predictor_golden_deepspeech2.json"), encoding="utf-8") as f:
+        g = json.load(f)
+    pred = build(tmp_path, "deepspeech2", synth.deepspeech2_state_dict(g["wseed"], streaming=True))
+    x = make_audio(g["kind"], g["aseed"], g["samples"])
+    whole = pred.predict(audio_data=x.copy())
+    assert whole["text"] == g["whole"]["text"] and abs(whole["score"] - g["whole"]["score"]) < 1e-3
+    pcm = (np.clip(x, -1, 1) * 32767).astype("<i2")
+    push = g["push"]
+    pred.reset_stream()
+    got = [pred.predict_stream(audio_data=pcm[s:s + push].tobytes(), is_end=s + push >= len(pcm)) for s in range(0, len(pcm), push)]
+    assert len(got) == len(g["pushes_pcm"])
+    for r, w in zip(got, g["pushes_pcm"]):
+        assert (r is None) == (w is None), (r, w)
+        if r is not None:
+            assert r["text"] == w["text"], (r, w)
+            assert abs(r["score"] - w["score"]) < 1e-3
