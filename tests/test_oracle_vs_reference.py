@@ -137,3 +137,38 @@ def test_efficient_conformer_chunk_forward_matches():
             assert (pr - pm).abs().max().item() < 5e-6
             assert att.shape == st.att_cache.shape and (att - st.att_cache).abs().max().item() < 2e-5
             assert cnn.shape == st.cnn_cache.shape and (cnn - st.cnn_cache).abs().max().item() < 2e-5
+
+
+def test_deepspeech2_chunk_forward_matches():
+    """oracle/deepspeech2.get_encoder_out with a carried (h, c) state against the live reference's
+    ``get_encoder_out_chunk`` (deepspeech2/model.py:70-77), window by window."""
+    ref_shims.install()
+    import tempfile
+    import yaml
+    from masr.model_utils.deepspeech2.model import DeepSpeech2Model
+    from oracle import deepspeech2 as od
+    cfg_y = yaml.safe_load(open(os.path.join(ref_shims.REFERENCE_ROOT, "configs", "deepspeech2.yml"), encoding="utf-8"))
+    with tempfile.TemporaryDirectory() as tmp:
+        mi = os.path.join(tmp, "mi.json")
+        synth.write_mean_istd(mi, 0)
+        m = DeepSpeech2Model(input_dim=80, vocab_size=synth.DEFAULT_VOCAB_SIZE, mean_istd_path=mi, streaming=True,
+                             encoder_conf=cfg_y["encoder_conf"], decoder_conf=cfg_y["decoder_conf"]).eval()
+    sdn = synth.deepspeech2_state_dict(0, streaming=True)
+    m.load_state_dict(synth.to_torch(sdn), strict=True)
+    sd = synth.to_torch(sdn)
+    cfg = od.DS2Config(bidirectional=False)
+    feat = torch.from_numpy(ob.featurize(make_audio("speech", 14, 16000 * 3 + 4000)))[None]
+    with torch.no_grad():
+        h = torch.zeros(0, 0, 0, 0)
+        c = torch.zeros(0, 0, 0, 0)
+        state = None
+        nf = feat.shape[1]
+        for cur in range(0, nf - 7 + 1, 64):
+            ch = feat[:, cur:min(cur + 67, nf)]
+            pr, lens, h, c = m.get_encoder_out_chunk(ch, torch.tensor([ch.shape[1]]), h, c)
+            pm, state = od.get_encoder_out(sd, cfg, ch, state)
+            assert pr.shape[1] == pm.shape[0] == int(lens[0])
+            assert torch.equal(pr[0].argmax(-1), pm.argmax(-1))
+            assert (pr[0] - pm).abs().max().item() < 5e-6
+            assert (h.reshape(-1) - state[0].reshape(-1)).abs().max().item() < 2e-5
+            assert (c.reshape(-1) - state[1].reshape(-1)).abs().max().item() < 2e-5
