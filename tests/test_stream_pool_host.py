@@ -121,3 +121,40 @@ def test_stream_pool_host_logic_matches_predict_stream(monkeypatch, predictor_go
     out = pool.push({1: pcms[1][:push * 3].tobytes()}, is_end=True)
     ref = oracle_predict_stream(sd, pcms[1][:push * 3], push * 3, vocab)
     assert out[1]["text"] == ref[-1]["text"]
+
+
+def test_stream_sessions_protocol(monkeypatch, predictor_golden):
+    """infer_server.py's websocket contract over the pool: replies after every non-empty message, `end` suffix closes the
+    utterance and frees the slot, no-resource answer when every slot is busy."""
+    from masr_b200 import serve
+    g = predictor_golden
+    sd = synth.to_torch(synth_weights(g["wseed"]))
+    vocab = synth.vocabulary()
+    monkeypatch.setattr(sp, "make_pool", lambda eng, n, max_frames=3000: OraclePool(sd, n))
+    sess = serve.StreamSessions(sp.StreamPool(OracleEngine(), vocab, n_slots=2))
+    a, b = sess.open(), sess.open()
+    assert a is not None and b is not None and a != b and sess.open() is None       # third connection: no resource
+    x = make_audio(g["kind"], g["aseed"], g["samples"])
+    pcm = (np.clip(x, -1, 1) * 32767).astype("<i2")
+    push = g["push"]
+    msgs = [pcm[s:s + push].tobytes() for s in range(0, len(pcm), push)]
+    msgs[-1] += b"end"
+    want_text, texts = "", []
+    for w in g["pushes_pcm"]:
+        if w is not None:
+            want_text = w["text"]
+        texts.append(want_text)
+    for k, m in enumerate(msgs):
+        batch = {a: m}
+        if k == 1:
+            batch[b] = b""                                    # empty message: ignored, no reply
+        rep = sess.feed(batch)
+        assert set(rep) == {a}
+        assert rep[a] == {"code": 0, "result": texts[k]}
+    assert a not in sess.text and len(sess.free) == 1          # closed by `end`
+    c = sess.open()
+    assert c == a                                              # the freed slot is reused with a clean state
+    rep = sess.feed({c: msgs[0], b: msgs[0]})
+    assert rep[c] == rep[b] == {"code": 0, "result": texts[0]}
+    with pytest.raises(KeyError):
+        sess.feed({99: b"xx"})
