@@ -49,6 +49,8 @@ def pack_deepspeech2(sd: Dict[str, torch.Tensor], device) -> DS2Weights:
 
     idim = sd["encoder.global_cmvn.mean"].shape[0]
     C = sd["encoder.conv.conv.0.weight"].shape[0]
+    from .weights import check_supported
+    check_supported(sd, "deepspeech2")
     H = sd["encoder.rnns.0.rnn.weight_hh_l0"].shape[1]
     dirs = 2 if "encoder.rnns.0.rnn.weight_hh_l0_reverse" in sd else 1
     nl = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("encoder.rnns."))

@@ -34,6 +34,15 @@ def subsampled_len(frames: int) -> int:
     return max(0, ((frames - 1) // 2 - 1) // 2)
 
 
+def check_max_len(out_lens: Sequence[int], max_len: int) -> None:
+    """``RelPositionalEncoding.position_encoding`` (embedding.py:95-97) asserts ``offset + size < max_len``: the
+    precomputed ``linear_pos(pe)`` tables have ``max_len`` rows and the attention kernels index them by key position, so a
+    longer utterance (>= 5000 subsampled frames, about 200 s) must fail here, not read past the table."""
+    m = max(out_lens) if len(out_lens) else 0
+    if max_len > 0 and m >= max_len:                  # max_len == 0: a model without a position table (DeepSpeech2)
+        raise AssertionError("offset: {} + x.shape[1]: {} is larger than the max_len: {}".format(0, m, max_len))
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -313,6 +322,8 @@ class ConformerEngine:
         F1 = (Fmax - 1) // 2
         T = subsampled_len(Fmax)
         tl = [subsampled_len(int(f)) for f in feat_lens]
+        if tlens_dev is None:                         # (graph replays: the caller checked the true lengths)
+            check_max_len(tl, self.w.max_len)
         ws = self._workspace(B, Fmax)
         if T == 0:
             return ws["x"][:0], tl, 0, ws
@@ -579,6 +590,7 @@ class ConformerEngine:
             Fpad = max(q, (max(frames) + q - 1) // q * q) if B else q
             tl1 = [subsampled_len(f) for f in frames]
             tl = [self.final_len(t) for t in tl1]
+            check_max_len(tl1, self.w.max_len)
             if B == 0 or max(tl) == 0:
                 item = (slot, B, 0, tl, 0, False)
             else:
@@ -633,6 +645,7 @@ class ConformerEngine:
         frames = [num_frames(n) for n in lengths]
         q = self.GRAPH_FRAME_QUANTUM
         Fpad = max(q, (max(frames) + q - 1) // q * q)
+        check_max_len([subsampled_len(f) for f in frames], self.w.max_len)
         g = self._graph_for(B, Fpad, use_db, target_db)
         offs = np.zeros(B + 1, np.int64)
         np.cumsum(lengths, out=offs[1:])
@@ -657,6 +670,7 @@ class ConformerEngine:
         T = self.final_len(subsampled_len(Fpad))
         tl1 = [subsampled_len(f) for f in frames]
         tl = [self.final_len(t) for t in tl1]
+        check_max_len(tl1, self.w.max_len)
         if max(tl) == 0:
             return GreedyResult([[] for _ in range(B)], [0.0] * B, None, np.zeros(B, np.int32), np.zeros(B, np.int32))
         g = self._graph_for(B, Fpad, use_db, target_db)

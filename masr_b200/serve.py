@@ -58,12 +58,16 @@ class StreamSessions:
             if not grp:
                 continue
             try:
-                out = self.pool.push(grp, is_end=is_end)
-            except Exception:                               # infer_server.py:130-137
+                out = self.pool.push(grp, is_end=is_end, on_error="return")
+                bad = set(getattr(self.pool, "last_errors", {}))
+            except Exception:                               # infer_server.py:130-137 (a failure of the whole batched step)
                 for s in grp:
                     replies[s] = dict(FAILED)
                 continue
             for s in grp:
+                if s in bad:                                # only the offending connection fails (its stream state is untouched)
+                    replies[s] = dict(FAILED)
+                    continue
                 if out.get(s) is not None:
                     self.text[s] = out[s]["text"]
                 replies[s] = {"code": 0, "result": self.text[s]}

@@ -550,73 +550,147 @@ class StreamPool:
     def _dev_index(self, idx: np.ndarray) -> torch.Tensor:
         return torch.from_numpy(idx).to(self.eng.device, non_blocking=False)
 
-    def push(self, audio: Dict[int, object], is_end: bool = False, channels: int = 1, samp_width: int = 2):
-        """audio: slot -> np.ndarray | PCM bytes (one push per slot).  -> slot -> {'text','score'} | None, exactly what
-        ``MASRPredictor.predict_stream(chunk, is_end)`` would return for that stream."""
-        eng, S, R = self.eng, self.S, self.RING
-        slots = sorted(audio)
-        for s in slots:
-            a = audio[s]
-            new = samples_to_float32(a) if isinstance(a, np.ndarray) else pcm_bytes_to_float32(a, channels, samp_width)
-            self.remained[s] = new if self.remained[s] is None else np.concatenate([self.remained[s], new])
-        # one batched fbank over every slot's un-consumed samples; the tail keeps the gain (predict.py:274)
-        feats, frames, status = eng.fbank([self.remained[s] for s in slots], self.use_db, self.target_db)
-        gains = eng.last_gain.cpu().numpy() if self.use_db else np.ones(len(slots), np.float32)
-        if np.any(status.cpu().numpy() != 0):
-            raise ValueError("无法将段规范化到目标dB，音频增益已经超过max_gain_db (300.0dB)")
-        Fmax = feats.shape[1]
+    def _grow_ring(self, need: int):
+        """Re-allocate the feature ring with room for `need` un-consumed frames per slot (a single message longer than the
+        ring — about 10 s — is legal: the reference's `predict_stream` accepts any message length)."""
+        R0, S = self.RING, self.S
+        R1 = R0
+        while R1 < need:
+            R1 *= 2
+        ring = torch.zeros(S * R1 + 1, 80, device=self.eng.device, dtype=torch.float32)
         src, dst = [], []
-        for j, s in enumerate(slots):
-            nf = frames[j]
-            if self.count[s] + nf > R:
-                raise AssertionError(f"stream slot {s}: more than {R} un-consumed feature frames")
-            if nf:
-                f = np.arange(nf, dtype=np.int64)
-                src.append(j * Fmax + f)
-                dst.append(s * R + (self.head[s] + self.count[s] + f) % R)
-                self.count[s] += nf
-            tail = self.remained[s][FRAME_SHIFT * nf:]
-            self.remained[s] = (tail * np.float32(gains[j])).astype(np.float32) if self.use_db else tail
-        if src:                                      # append the new frames of every slot to the ring: one gather + one scatter
-            self.ring.index_copy_(0, self._dev_index(np.concatenate(dst)),
-                                  feats.view(-1, 80).index_select(0, self._dev_index(np.concatenate(src))))
-        pending = {s: chunk_starts(self.count[s], is_end) for s in slots}
-        ends = {}
-        rounds = max((len(v) for v in pending.values()), default=0)
-        zero_row = S * R
-        win = np.arange(CHUNK_FRAMES, dtype=np.int64)
-        for r in range(rounds):
-            nfr = [0] * S
-            idx = np.full((S, CHUNK_FRAMES), zero_row, np.int64)
-            for s in slots:
-                if r < len(pending[s]):
-                    cur = pending[s][r]
-                    end = min(cur + CHUNK_FRAMES, self.count[s])
-                    n = end - cur
-                    idx[s, :n] = s * R + (self.head[s] + cur + win[:n]) % R
-                    nfr[s] = n
-                    ends[s] = end
-            batch = self.ring.index_select(0, self._dev_index(idx.reshape(-1))).view(S, CHUNK_FRAMES, 80)
-            ids, maxp, tout = self.pool.step(batch, nfr)
-            ids_h, mp_h = ids.cpu().numpy(), maxp.cpu().numpy()
-            for s in slots:
-                prev, acc, toks = self.prev[s], self.acc[s], self.toks[s]
-                for t in range(tout[s]):
-                    i = int(ids_h[s, t])
-                    if i != 0:
-                        acc = np.float32(acc + mp_h[s, t])
-                        self.nprob[s] += 1
-                        if i != prev:
-                            toks.append(i)
-                    prev = i
-                self.prev[s], self.acc[s] = prev, acc
-        out = {}
-        for s in slots:
-            if not pending[s]:
-                out[s] = None
+        for s in range(S):
+            if self.count[s]:
+                f = np.arange(self.count[s], dtype=np.int64)
+                src.append(s * R0 + (self.head[s] + f) % R0)
+                dst.append(s * R1 + f)
+            self.head[s] = 0
+        if src:
+            ring.index_copy_(0, self._dev_index(np.concatenate(dst)), self.ring.index_select(0, self._dev_index(np.concatenate(src))))
+        self.ring, self.RING = ring, R1
+
+    def push(self, audio: Dict[int, object], is_end: bool = False, channels: int = 1, samp_width: int = 2,
+             on_error: str = "raise"):
+        """audio: slot -> np.ndarray | PCM bytes (one push per slot).  -> slot -> {'text','score'} | None, exactly what
+        ``MASRPredictor.predict_stream(chunk, is_end)`` would return for that stream.
+
+        Per-slot isolation: every slot is validated (decodable input, gain within 300 dB, pool / position-table capacity,
+        no chunk after a short final chunk) BEFORE any state changes; a slot that fails keeps its previous state, is left
+        out of the batched rounds and its exception lands in ``self.last_errors[slot]`` — the other slots of the push are
+        decoded normally, as the reference only fails the offending connection (infer_server.py:130-137).
+        ``on_error="raise"`` then raises ``StreamSlotError`` (carrying ``errors`` and the healthy slots' ``results``);
+        ``on_error="return"`` returns the healthy slots' results only."""
+        eng, S = self.eng, self.S
+        self.last_errors = {}
+        errors = self.last_errors
+        cand = {}
+        for s in sorted(audio):
+            a = audio[s]
+            try:
+                new = samples_to_float32(a) if isinstance(a, np.ndarray) else pcm_bytes_to_float32(a, channels, samp_width)
+            except Exception as e:                    # undecodable message: only this slot fails
+                errors[s] = e
                 continue
-            consumed = ends[s] - CACHED_FEATURE_NUM              # predict.py:330: keep the last 3 frames of the window
-            self.head[s] = (self.head[s] + consumed) % R
-            self.count[s] -= consumed
-            out[s] = {"text": ids_to_text(self.toks[s], self.vocab), "score": greedy_score(self.acc[s], self.nprob[s])}
+            cand[s] = new if self.remained[s] is None else np.concatenate([self.remained[s], new])
+        slots = sorted(cand)
+        out: Dict[int, Optional[dict]] = {}
+        if slots:
+            # one batched fbank over every slot's un-consumed samples; the tail keeps the gain (predict.py:274)
+            feats, frames, status = eng.fbank([cand[s] for s in slots], self.use_db, self.target_db)
+            gains = eng.last_gain.cpu().numpy() if self.use_db else np.ones(len(slots), np.float32)
+            status_h = status.cpu().numpy()
+            Fmax = feats.shape[1]
+            pool = self.pool
+            cap = getattr(pool, "cap", None)
+            max_len = getattr(getattr(eng, "w", None), "max_len", None)
+            lens_host = getattr(pool, "lens_host", None)
+            short_once = bool(getattr(pool, "SHORT_ONCE", False))
+            good, pending = [], {}
+            for j, s in enumerate(slots):
+                if status_h[j] != 0:
+                    errors[s] = ValueError("无法将段规范化到目标dB，音频增益已经超过max_gain_db (300.0dB)")
+                    continue
+                total = self.count[s] + frames[j]
+                starts = chunk_starts(total, is_end)
+                if lens_host is not None and starts:
+                    new_out = sum(subsampled_len(min(c + CHUNK_FRAMES, total) - c) for c in starts)
+                    have = lens_host[s]
+                    if short_once and have % CHUNK_OUT and new_out:
+                        errors[s] = AssertionError(f"stream slot {s}: a short (final) chunk was already decoded; reset the stream first")
+                        continue
+                    if (cap is not None and have + new_out > cap) or (max_len is not None and have + new_out >= max_len):
+                        errors[s] = AssertionError("offset: {} + x.shape[1]: {} is larger than the max_len: {}".format(
+                            have, new_out, min(v for v in (cap, max_len) if v is not None)))
+                        continue
+                good.append((j, s))
+                pending[s] = starts
+            need = max((self.count[s] + frames[j] for j, s in good), default=0)
+            if need > self.RING:
+                self._grow_ring(need)
+            R = self.RING
+            # ---- commit: nothing below can fail for a validated slot ----
+            src, dst = [], []
+            for j, s in good:
+                nf = frames[j]
+                if nf:
+                    f = np.arange(nf, dtype=np.int64)
+                    src.append(j * Fmax + f)
+                    dst.append(s * R + (self.head[s] + self.count[s] + f) % R)
+                tail = cand[s][FRAME_SHIFT * nf:]
+                self.remained[s] = (tail * np.float32(gains[j])).astype(np.float32) if self.use_db else tail
+            if src:                                  # append the new frames of every slot to the ring: one gather + one scatter
+                self.ring.index_copy_(0, self._dev_index(np.concatenate(dst)),
+                                      feats.view(-1, 80).index_select(0, self._dev_index(np.concatenate(src))))
+            for j, s in good:
+                self.count[s] += frames[j]
+            live = [s for _, s in good]
+            ends = {}
+            rounds = max((len(v) for v in pending.values()), default=0)
+            zero_row = S * R
+            win = np.arange(CHUNK_FRAMES, dtype=np.int64)
+            for r in range(rounds):
+                nfr = [0] * S
+                idx = np.full((S, CHUNK_FRAMES), zero_row, np.int64)
+                for s in live:
+                    if r < len(pending[s]):
+                        cur = pending[s][r]
+                        end = min(cur + CHUNK_FRAMES, self.count[s])
+                        n = end - cur
+                        idx[s, :n] = s * R + (self.head[s] + cur + win[:n]) % R
+                        nfr[s] = n
+                        ends[s] = end
+                batch = self.ring.index_select(0, self._dev_index(idx.reshape(-1))).view(S, CHUNK_FRAMES, 80)
+                ids, maxp, tout = self.pool.step(batch, nfr)
+                ids_h, mp_h = ids.cpu().numpy(), maxp.cpu().numpy()
+                for s in live:
+                    prev, acc, toks = self.prev[s], self.acc[s], self.toks[s]
+                    for t in range(tout[s]):
+                        i = int(ids_h[s, t])
+                        if i != 0:
+                            acc = np.float32(acc + mp_h[s, t])
+                            self.nprob[s] += 1
+                            if i != prev:
+                                toks.append(i)
+                        prev = i
+                    self.prev[s], self.acc[s] = prev, acc
+            for s in live:
+                if not pending[s]:
+                    out[s] = None
+                    continue
+                consumed = ends[s] - CACHED_FEATURE_NUM              # predict.py:330: keep the last 3 frames of the window
+                self.head[s] = (self.head[s] + consumed) % R
+                self.count[s] -= consumed
+                out[s] = {"text": ids_to_text(self.toks[s], self.vocab), "score": greedy_score(self.acc[s], self.nprob[s])}
+        if errors and on_error == "raise":
+            raise StreamSlotError(errors, out)
         return out
+
+
+class StreamSlotError(Exception):
+    """Some slots of a ``StreamPool.push`` failed: ``errors`` maps slot -> exception, ``results`` holds what the healthy
+    slots returned (their state advanced normally)."""
+
+    def __init__(self, errors: Dict[int, Exception], results: Dict[int, Optional[dict]]):
+        self.errors, self.results = dict(errors), dict(results)
+        first = next(iter(self.errors.values()))
+        super().__init__(f"{len(self.errors)} stream slot(s) failed: slot {next(iter(self.errors))}: {first}")

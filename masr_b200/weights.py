@@ -111,8 +111,38 @@ class ConformerWeights:
     ctc_b: torch.Tensor = None
 
 
+class UnsupportedConfig(ValueError):
+    """The checkpoint comes from a reference configuration this build has no kernels for."""
+
+
+def check_supported(sd: Dict[str, torch.Tensor], family: str = "conformer") -> None:
+    """Fail loudly on supported-by-the-reference variants this build does not implement, instead of mis-packing them
+    (the packers read architecture from tensor names and shapes): ``cnn_module_norm='batch_norm'`` in a Conformer /
+    EfficientConformer (convolution.py:60-63: same ``conv_module.norm.weight`` key as the LayerNorm variant, plus running
+    statistics), ``input_layer`` conv2d6 / conv2d8 (subsampling.py:115-236: extra ``embed.conv.4``), GRU recurrences in
+    DeepSpeech2 (deepspeech2/encoder.py:19-33), attention heads that are not 64 wide."""
+    keys = sd.keys()
+    if family in ("conformer", "efficient_conformer") and any(k.endswith("conv_module.norm.running_mean") for k in keys):
+        raise UnsupportedConfig("unsupported config: cnn_module_norm='batch_norm' (this build implements the shipped "
+                                "layer_norm conv module for conformer / efficient_conformer)")
+    if any(k.startswith("encoder.embed.conv.4.") for k in keys):
+        raise UnsupportedConfig("unsupported config: input_layer conv2d6/conv2d8 (this build implements conv2d = Conv2dSubsampling4)")
+    if family == "deepspeech2":
+        hh = sd.get("encoder.rnns.0.rnn.weight_hh_l0")
+        if hh is not None and hh.shape[0] != 4 * hh.shape[1]:          # GRU: 3 gates, LSTM: 4
+            raise UnsupportedConfig("unsupported config: use_gru=True (this build implements the shipped LSTM recurrences)")
+        return
+    u = sd.get("encoder.encoders.0.self_attn.pos_bias_u")
+    if u is not None:
+        d = sd["encoder.after_norm.weight"].shape[0]
+        if d % u.shape[0] or d // u.shape[0] != 64:
+            raise UnsupportedConfig(f"unsupported config: attention heads of width {d / u.shape[0]:g} (this build: d_k = 64, "
+                                    "e.g. output_size 256 / attention_heads 4)")
+
+
 def pack_conformer(sd: Dict[str, torch.Tensor], device, max_len: int = 5000) -> ConformerWeights:
     dev = torch.device(device)
+    check_supported(sd, "conformer")
 
     def D(t):
         return t.contiguous().to(dev)

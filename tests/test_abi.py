@@ -73,3 +73,35 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_max_len_guard_matches_the_reference_assert():
+    """utterances whose subsampled length reaches the position table (embedding.py:95-97) fail on the host."""
+    import pytest
+    from masr_b200.engine import check_max_len, num_frames, subsampled_len
+    check_max_len([], 5000)
+    check_max_len([0, 4999], 5000)
+    check_max_len([123456], 0)                       # DeepSpeech2: no position table
+    n = 16000 * 201
+    assert subsampled_len(num_frames(n)) >= 5000
+    with pytest.raises(AssertionError, match="larger than the max_len: 5000"):
+        check_max_len([10, subsampled_len(num_frames(n))], 5000)
+
+
+def test_unsupported_reference_variants_are_rejected_not_mispacked():
+    """batch_norm conv modules, conv2d6/8 front-ends, GRU DeepSpeech2 and odd head widths raise a clear error."""
+    import numpy as np
+    import pytest
+    import torch
+    from masr_b200.weights import UnsupportedConfig, check_supported
+    base = {"encoder.after_norm.weight": torch.zeros(256), "encoder.encoders.0.self_attn.pos_bias_u": torch.zeros(4, 64)}
+    check_supported(base)
+    with pytest.raises(UnsupportedConfig, match="batch_norm"):
+        check_supported({**base, "encoder.encoders.0.conv_module.norm.running_mean": torch.zeros(256)})
+    with pytest.raises(UnsupportedConfig, match="conv2d6"):
+        check_supported({**base, "encoder.embed.conv.4.weight": torch.zeros(1)})
+    with pytest.raises(UnsupportedConfig, match="heads"):
+        check_supported({**base, "encoder.encoders.0.self_attn.pos_bias_u": torch.zeros(8, 32)})
+    with pytest.raises(UnsupportedConfig, match="use_gru"):
+        check_supported({"encoder.rnns.0.rnn.weight_hh_l0": torch.zeros(3 * 16, 16)}, "deepspeech2")
+    check_supported({"encoder.rnns.0.rnn.weight_hh_l0": torch.zeros(4 * 16, 16)}, "deepspeech2")

@@ -23,17 +23,22 @@ class OracleEngine:
         self.last_gain = None
 
     def fbank(self, waves, use_db=True, target_db=-20.0):
-        feats, frames, gains = [], [], []
+        feats, frames, gains, status = [], [], [], []
         for w in waves:
-            x, g = ob.normalize_gain(np.asarray(w, np.float32).copy(), target_db) if use_db else (w, np.float32(1))
-            f = ob.kaldi_fbank(ob.to_int16(x))
+            try:
+                x, g = ob.normalize_gain(np.asarray(w, np.float32).copy(), target_db) if use_db else (w, np.float32(1))
+                status.append(0)
+            except ValueError:                     # the CUDA front-end reports > 300 dB as a per-utterance status flag
+                x, g = np.zeros(0, np.float32), np.float32(1)
+                status.append(1)
+            f = ob.kaldi_fbank(ob.to_int16(x)) if x.shape[0] >= 400 else np.zeros((0, 80), np.float32)
             feats.append(f); frames.append(f.shape[0]); gains.append(g)
         Fmax = max(1, max(frames))
         out = torch.zeros(len(waves), Fmax, 80)
         for i, f in enumerate(feats):
             out[i, :f.shape[0]] = torch.from_numpy(f)
         self.last_gain = torch.tensor(gains, dtype=torch.float32)
-        return out, frames, torch.zeros(len(waves), dtype=torch.int32)
+        return out, frames, torch.tensor(status, dtype=torch.int32)
 
 
 class OraclePool:
@@ -158,3 +163,50 @@ def test_stream_sessions_protocol(monkeypatch, predictor_golden):
     assert rep[c] == rep[b] == {"code": 0, "result": texts[0]}
     with pytest.raises(KeyError):
         sess.feed({99: b"xx"})
+
+
+def test_push_isolates_a_failing_slot_and_grows_the_ring(monkeypatch, predictor_golden):
+    """a slot that cannot be decoded (gain above 300 dB, capacity, garbage input) must fail ALONE — its state
+    untouched, the other slots of the same push decoded normally and identically to a push without the bad slot; a
+    single message longer than the feature ring (about 10 s) is consumed like the reference consumes it."""
+    from masr_b200 import serve
+    g = predictor_golden
+    sd = synth.to_torch(synth_weights(g["wseed"]))
+    vocab = synth.vocabulary()
+    monkeypatch.setattr(sp, "make_pool", lambda eng, n, max_frames=3000: OraclePool(sd, n))
+    x = make_audio(g["kind"], g["aseed"], g["samples"])
+    pcm = (np.clip(x, -1, 1) * 32767).astype("<i2")
+    push = g["push"]
+    silent = np.full(8000, 1e-20, np.float32)                  # needs > 300 dB of gain -> ValueError in the reference
+
+    clean = sp.StreamPool(OracleEngine(), vocab, n_slots=2)
+    mixed = sp.StreamPool(OracleEngine(), vocab, n_slots=2)
+    nmsg = len(range(0, len(pcm), push))
+    for k in range(nmsg):
+        m = pcm[k * push:(k + 1) * push].tobytes()
+        want = clean.push({0: m}, is_end=k == nmsg - 1)
+        if k == 1:
+            with pytest.raises(sp.StreamSlotError) as ei:
+                mixed.push({0: m, 1: silent}, is_end=False)
+            assert set(ei.value.errors) == {1} and isinstance(ei.value.errors[1], ValueError)
+            got = ei.value.results
+        else:
+            got = mixed.push({0: m, 1: silent}, is_end=k == nmsg - 1, on_error="return")
+            assert set(mixed.last_errors) == {1}
+        assert got == want                                     # the healthy slot is unaffected, push by push
+        assert mixed.remained[1] is None and mixed.count[1] == 0 and mixed.toks[1] == []     # failing slot: state untouched
+    # the serving layer fails only the offending session
+    sess = serve.StreamSessions(sp.StreamPool(OracleEngine(), vocab, n_slots=2))
+    a, b = sess.open(), sess.open()
+    rep = sess.feed({a: pcm[:push].tobytes(), b: b"\x01"})     # odd byte count: not int16 PCM
+    assert rep[b] == serve.FAILED and rep[a]["code"] == 0
+    # one 12 s message (1198 frames > RING = 1024): same result as the single-stream oracle fed the same message
+    long_pcm = (np.clip(make_audio("speech", 97, 16000 * 12), -1, 1) * 32767).astype("<i2")
+    pool = sp.StreamPool(OracleEngine(), vocab, n_slots=2)
+    first = pool.push({0: pcm[:push].tobytes()}, is_end=False)                     # slot 0 mid-utterance while the ring grows
+    out = pool.push({1: long_pcm.tobytes()}, is_end=True)
+    ref = oracle_predict_stream(sd, long_pcm, len(long_pcm), vocab)
+    assert pool.RING >= 2048 and out[1]["text"] == ref[-1]["text"] and abs(out[1]["score"] - ref[-1]["score"]) < 1e-4
+    rest = pool.push({0: pcm[push:2 * push].tobytes()}, is_end=False)
+    c2 = sp.StreamPool(OracleEngine(), vocab, n_slots=1)
+    assert c2.push({0: pcm[:push].tobytes()}) == first and c2.push({0: pcm[push:2 * push].tobytes()}) == rest
