@@ -110,6 +110,29 @@ int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, const void* 
                        const float* bias, const float* residual, int64_t ldr, float* C, void* Ch, void* Cl,
                        int64_t ldc, int M, int N, int K, int epilogue, float alpha, void* stream);
 
+/* Sub-layer output projection (N = 256) + residual add + the LayerNorm(s) that follow it, in ONE tensor-core kernel:
+ *   x_new = residual + alpha * (A.W^T + bias)
+ *   gamma2 == NULL:  X <- x_new,                      (Yh, Yl) <- LN(x_new; gamma1, beta1)
+ *                    (conformer/encoder.py:117 -> 122, 131 -> 141, 145 -> 153: the next sub-layer's pre-norm)
+ *   gamma2 != NULL:  X <- LN(x_new; gamma1, beta1),   (Yh, Yl) <- LN(X; gamma2, beta2)
+ *                    (encoder.py:155 -> 161 `norm_final` -> the next block's 106 `norm_ff_macaron`, or :342 `after_norm`)
+ *   Y2 (optional): fp32 copy of what the pair holds.  X, Y2, Yh, Yl share the row pitch ldx; X may alias residual.
+ * Launched as clusters of 2 CTAs (the two 128-column tiles of a row block); the row statistics (two-pass mean / centred
+ * variance) cross the pair through distributed shared memory.  Same results as masr_gemm_tc_f16x2(MASR_EPI_RESIDUAL)
+ * followed by masr_layernorm_split_f16 / masr_layernorm2_split_f16 up to the summation order of the statistics. */
+int masr_gemm_tc_residual_ln_f16x2(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl,
+                                   const float* bias, const float* residual, int64_t ldr, float alpha, float* X,
+                                   const float* gamma1, const float* beta1, const float* gamma2, const float* beta2,
+                                   float* Y2, void* Yh, void* Yl, int64_t ldx, int M, int N, int K, float eps, void* stream);
+
+/* CTC head without the [M, V] logits: ctc_lo Linear (loss/ctc.py:70) with a GEMM epilogue that keeps, per frame and per
+ * 32-column group, (max logit, first argmax, sum exp(x - max)), then a combine kernel -> per-frame argmax id (first
+ * maximum, ctc_greedy_decoder.py:21) and max-probability 1 / sum_j exp(x_j - max) (the softmax value of the argmax).
+ * workspace: 3 * ceil(V/32) * M * 4 bytes.  Same outputs as masr_gemm_tc_f16x2 + masr_ctc_frame_argmax_f32. */
+int masr_ctc_head_argmax_tc_f16x2(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl,
+                                  const float* bias, int M, int V, int K, void* workspace, int64_t workspace_bytes,
+                                  int* ids, float* maxp, void* stream);
+
 /* Conv2dSubsampling4's first conv (as masr_conv1_cmvn_relu_f32) written as fp16 (h,l) pairs in four
  * (t,f)-parity planes [4][B][(F1max+1)/2][20][C], and its second conv + ReLU (subsampling.py:83-84) as a
  * tensor-core implicit GEMM over those planes: the stride-2 window of tap (kh,kw) is a dense TMA box of plane

@@ -148,7 +148,21 @@ struct TcParams {
     // conv mode (implicit GEMM over parity planes of the conv-1 activation)
     int conv_T2;       // output rows per utterance (T2max)
     int flags;         // bit 0: stage epilogue stores through shared memory (row-contiguous global writes)
+    // MASR_EPI_RESIDUAL_LN / _LN2 (cluster kernel): LayerNorm(s) of the finished 256-wide row fused behind the residual add
+    const float* ln_g;
+    const float* ln_b;
+    const float* ln_g2;
+    const float* ln_b2;
+    float* y2;         // optional fp32 copy of the last LayerNorm's output (row pitch ldc)
+    float ln_eps;
+    // MASR_EPI_CTC_PARTIAL: per (row, 32-column group) softmax partials [group][M] instead of logits
+    float* part_m;
+    float* part_s;
+    int* part_i;
 };
+
+// internal epilogue codes (continuing include/masr_b200.h's MASR_EPI_*)
+constexpr int EPI_RESIDUAL_LN = 6, EPI_RESIDUAL_LN2 = 7, EPI_CTC_PARTIAL = 8;
 
 struct TcMaps {
     CUtensorMap a[8];  // GEMM: a[0]=Ah, a[1]=Al.  CONV: a[2*plane + {0:h,1:l}], plane = (kh&1)*2 + (kw&1)
@@ -236,77 +250,181 @@ __device__ __forceinline__ void staged_load(const EpiCtx& c, uint4 (&regs)[8], c
     for (int k2 = 0; k2 < 8; ++k2) regs[k2] = lds128(c.sb + c.lane * 128 + ((k2 ^ (c.lane & 7)) << 4));
 }
 
-// W fp32 outputs of this thread's row (W = 32, or 16 after GLU) at output column n -> fp32 C and/or (h,l) pair
-template <int W, bool BIG>
-__device__ __forceinline__ void emit(const TcParams& p, const EpiCtx& c, const float (&o)[W], int n, int n_limit) {
+// W fp32 values of this thread's row (W = 32, or 16 after GLU) at output column n -> fp32 rows at C (pitch ld).
+// STG = bytes of this warp's staging buffer (4096 / 2048 / 1024): a row segment goes through it in pieces of STG/512 chunks.
+template <int W, int STG>
+__device__ __forceinline__ void emit_f32(const EpiCtx& c, float* C, int64_t ld, int flags, const float (&o)[W], int n, int n_limit) {
     const bool full = n + W - 1 < n_limit;
     const bool row_ok = c.lane < c.nvalid;
     const int64_t my_row = c.row0 + c.lane;
-    if (p.C) {
-        if ((p.flags & 1) && full && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
-            constexpr int CH = (W == 32 && !BIG) ? 4 : W / 4;     // 2 KB staging: a 32-wide fp32 block goes in two halves
+    if ((flags & 1) && full && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+        constexpr int CH = (W / 4 < STG / 512) ? W / 4 : STG / 512;
 #pragma unroll
-            for (int part = 0; part < (W / 4) / CH; ++part) {
-                uint4 regs[CH];
+        for (int part = 0; part < (W / 4) / CH; ++part) {
+            uint4 regs[CH];
 #pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const int e = (part * CH + j) * 4;
-                    regs[j] = make_uint4(__float_as_uint(o[e]), __float_as_uint(o[e + 1]), __float_as_uint(o[e + 2]), __float_as_uint(o[e + 3]));
-                }
-                staged_store<CH>(c, regs, reinterpret_cast<uint8_t*>(p.C + c.row0 * p.ldc + n + part * CH * 4), p.ldc * 4);
+            for (int j = 0; j < CH; ++j) {
+                const int e = (part * CH + j) * 4;
+                regs[j] = make_uint4(__float_as_uint(o[e]), __float_as_uint(o[e + 1]), __float_as_uint(o[e + 2]), __float_as_uint(o[e + 3]));
             }
-        } else if (row_ok && full && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
-            float* cp = p.C + my_row * p.ldc + n;
-#pragma unroll
-            for (int j = 0; j < W; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-        } else if (row_ok) {
-            float* cp = p.C + my_row * p.ldc + n;
-#pragma unroll
-            for (int j = 0; j < W; ++j)
-                if (n + j < n_limit) cp[j] = o[j];
+            staged_store<CH>(c, regs, reinterpret_cast<uint8_t*>(C + c.row0 * ld + n + part * CH * 4), ld * 4);
         }
+    } else if (row_ok && full && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+        float* cp = C + my_row * ld + n;
+#pragma unroll
+        for (int j = 0; j < W; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    } else if (row_ok) {
+        float* cp = C + my_row * ld + n;
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if (n + j < n_limit) cp[j] = o[j];
     }
-    if (p.Ch) {
-        uint32_t hh[W / 2], ll[W / 2];                       // packed half2 bit patterns (kept in registers)
+}
+
+// ... -> the fp16 (h, l) operand pair the next GEMM consumes
+template <int W, int STG>
+__device__ __forceinline__ void emit_pair(const EpiCtx& c, __half* Ch, __half* Cl, int64_t ld, int flags, const float (&o)[W], int n,
+                                          int n_limit) {
+    const bool full = n + W - 1 < n_limit;
+    const bool row_ok = c.lane < c.nvalid;
+    const int64_t my_row = c.row0 + c.lane;
+    uint32_t hh[W / 2], ll[W / 2];                       // packed half2 bit patterns (kept in registers)
+#pragma unroll
+    for (int j = 0; j < W / 2; ++j) {
+        __half2 h2, l2;
+        split_f16x2(o[2 * j], o[2 * j + 1], h2, l2);
+        hh[j] = *reinterpret_cast<uint32_t*>(&h2);
+        ll[j] = *reinterpret_cast<uint32_t*>(&l2);
+    }
+    const bool aligned = (ld & 7) == 0 && ((reinterpret_cast<uintptr_t>(Ch) | reinterpret_cast<uintptr_t>(Cl)) & 15) == 0;
+    if ((flags & 1) && full && aligned) {
+        constexpr int CH = (W / 8 < STG / 512) ? W / 8 : STG / 512;
+#pragma unroll
+        for (int part = 0; part < (W / 8) / CH; ++part) {
+            uint4 regs[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) { const int e = 4 * (part * CH + j); regs[j] = make_uint4(hh[e], hh[e + 1], hh[e + 2], hh[e + 3]); }
+            staged_store<CH>(c, regs, reinterpret_cast<uint8_t*>(Ch + c.row0 * ld + n + part * CH * 8), ld * 2);
+#pragma unroll
+            for (int j = 0; j < CH; ++j) { const int e = 4 * (part * CH + j); regs[j] = make_uint4(ll[e], ll[e + 1], ll[e + 2], ll[e + 3]); }
+            staged_store<CH>(c, regs, reinterpret_cast<uint8_t*>(Cl + c.row0 * ld + n + part * CH * 8), ld * 2);
+        }
+    } else if (row_ok && full && aligned) {
+        uint4* hp = reinterpret_cast<uint4*>(Ch + my_row * ld + n);
+        uint4* lp = reinterpret_cast<uint4*>(Cl + my_row * ld + n);
+#pragma unroll
+        for (int j = 0; j < W / 8; ++j) {
+            hp[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
+            lp[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
+        }
+    } else if (row_ok) {
+        unsigned short* hp = reinterpret_cast<unsigned short*>(Ch + my_row * ld + n);
+        unsigned short* lp = reinterpret_cast<unsigned short*>(Cl + my_row * ld + n);
 #pragma unroll
         for (int j = 0; j < W / 2; ++j) {
-            __half2 h2, l2;
-            split_f16x2(o[2 * j], o[2 * j + 1], h2, l2);
-            hh[j] = *reinterpret_cast<uint32_t*>(&h2);
-            ll[j] = *reinterpret_cast<uint32_t*>(&l2);
+            if (n + 2 * j < n_limit) { hp[2 * j] = (unsigned short)(hh[j] & 0xffff); lp[2 * j] = (unsigned short)(ll[j] & 0xffff); }
+            if (n + 2 * j + 1 < n_limit) { hp[2 * j + 1] = (unsigned short)(hh[j] >> 16); lp[2 * j + 1] = (unsigned short)(ll[j] >> 16); }
         }
-        if ((p.flags & 1) && full && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.Ch) | reinterpret_cast<uintptr_t>(p.Cl)) & 15) == 0) {
-            uint4 regs[W / 8];
+    }
+}
+
+template <int W, int STG>
+__device__ __forceinline__ void emit(const TcParams& p, const EpiCtx& c, const float (&o)[W], int n, int n_limit) {
+    if (p.C) emit_f32<W, STG>(c, p.C, p.ldc, p.flags, o, n, n_limit);
+    if (p.Ch) emit_pair<W, STG>(c, p.Ch, p.Cl, p.ldc, p.flags, o, n, n_limit);
+}
+
+// ---- LayerNorm fused behind the residual epilogue (cluster of 2 CTAs) --------------------------------------------------------
+// A 256-wide output row is spread over 2 CTAs (the two 128-column tiles of one row block = one cluster) x 4 epilogue warps
+// (32 columns each), one thread per (row, 32 columns).  Row statistics are exchanged through distributed shared memory:
+// every thread stores its partial into BOTH CTAs' `red[buf][src cta][column group][row]`, one lane per warp arrives
+// (release.cluster) on both CTAs' mbarrier, everybody waits on its own (acquire.cluster) and sums the 8 partials in a fixed
+// order — both CTAs obtain bit-identical statistics.  Two-pass (mean, then centred variance) like norm.cu; rounds alternate
+// between two buffers / two barriers, so a fast warp can never overwrite or complete a round that a slow one still reads.
+struct LnCtx {
+    uint32_t red, red_peer;      // shared::cta / shared::cluster byte addresses of red[2][2][4][128] floats
+    uint32_t bar, bar_peer;      // ... of the two mbarriers
+    uint32_t rank, cgrp, row, lane;
+    uint32_t round;
+};
+
+__device__ __forceinline__ float ln_exchange(LnCtx& L, float val) {
+    const uint32_t buf = L.round & 1;
+    const uint32_t off = ((((buf * 2 + L.rank) * 4 + L.cgrp) * 128) + L.row) * 4;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(L.red + off), "f"(val) : "memory");
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(L.red_peer + off), "f"(val) : "memory");
+    __syncwarp();
+    if (L.lane == 0) {
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(L.bar + buf * 8) : "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(L.bar_peer + buf * 8) : "memory");
+    }
+    const uint32_t parity = (L.round >> 1) & 1;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LN_WAIT:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra LN_DONE;\n\t"
+        "bra LN_WAIT;\n\t"
+        "LN_DONE:\n\t"
+        "}" ::"r"(L.bar + buf * 8), "r"(parity) : "memory");
+    float tot = 0.f;
 #pragma unroll
-            for (int j = 0; j < W / 8; ++j) regs[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
-            staged_store<W / 8>(c, regs, reinterpret_cast<uint8_t*>(p.Ch + c.row0 * p.ldc + n), p.ldc * 2);
+    for (int k = 0; k < 8; ++k) {
+        float t;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(L.red + (((buf * 8 + k) * 128) + L.row) * 4) : "memory");
+        tot += t;
+    }
+    ++L.round;
+    return tot;
+}
+
+// o = LayerNorm(v) * gamma + beta over the 256-wide row this thread holds 32 columns of (g, b: pointers to those columns)
+__device__ __forceinline__ void ln_apply(LnCtx& L, const float (&v)[32], float (&o)[32], const float* g, const float* b, float eps) {
+    float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < W / 8; ++j) regs[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
-            staged_store<W / 8>(c, regs, reinterpret_cast<uint8_t*>(p.Cl + c.row0 * p.ldc + n), p.ldc * 2);
-        } else if (row_ok && full && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.Ch) | reinterpret_cast<uintptr_t>(p.Cl)) & 15) == 0) {
-            uint4* hp = reinterpret_cast<uint4*>(p.Ch + my_row * p.ldc + n);
-            uint4* lp = reinterpret_cast<uint4*>(p.Cl + my_row * p.ldc + n);
+    for (int j = 0; j < 32; j += 4) s += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+    const float mean = ln_exchange(L, s) * (1.0f / 256.0f);
+    float q = 0.f;
 #pragma unroll
-            for (int j = 0; j < W / 8; ++j) {
-                hp[j] = make_uint4(hh[4 * j], hh[4 * j + 1], hh[4 * j + 2], hh[4 * j + 3]);
-                lp[j] = make_uint4(ll[4 * j], ll[4 * j + 1], ll[4 * j + 2], ll[4 * j + 3]);
-            }
-        } else if (row_ok) {
-            unsigned short* hp = reinterpret_cast<unsigned short*>(p.Ch + my_row * p.ldc + n);
-            unsigned short* lp = reinterpret_cast<unsigned short*>(p.Cl + my_row * p.ldc + n);
+    for (int j = 0; j < 32; j += 4) {
+        const float a0 = v[j] - mean, a1 = v[j + 1] - mean, a2 = v[j + 2] - mean, a3 = v[j + 3] - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float rstd = rsqrtf(ln_exchange(L, q) * (1.0f / 256.0f) + eps);
 #pragma unroll
-            for (int j = 0; j < W / 2; ++j) {
-                if (n + 2 * j < n_limit) { hp[2 * j] = (unsigned short)(hh[j] & 0xffff); lp[2 * j] = (unsigned short)(ll[j] & 0xffff); }
-                if (n + 2 * j + 1 < n_limit) { hp[2 * j + 1] = (unsigned short)(hh[j] >> 16); lp[2 * j + 1] = (unsigned short)(ll[j] >> 16); }
-            }
-        }
+    for (int j = 0; j < 32; j += 4) {
+        const float4 gg = ldg_f4(g + j), bb = ldg_f4(b + j);          // warp-uniform addresses: one broadcast transaction
+        o[j] = (v[j] - mean) * rstd * gg.x + bb.x;
+        o[j + 1] = (v[j + 1] - mean) * rstd * gg.y + bb.y;
+        o[j + 2] = (v[j + 2] - mean) * rstd * gg.z + bb.z;
+        o[j + 3] = (v[j + 3] - mean) * rstd * gg.w + bb.w;
     }
 }
 
 // One 32-column slice of a finished output row: bias was already added; apply the epilogue and store.
 // `n` is the global column of v[0] (warp-uniform).
-template <bool BIG>
-__device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, float (&v)[32], int n) {
+template <int STG, bool LNC>
+__device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, float (&v)[32], int n, LnCtx& L) {
+    constexpr bool BIG = STG >= 4096;
+    if (!LNC && p.epi == EPI_CTC_PARTIAL) {
+        // CTC head (loss/ctc.py:70 softmax + ctc_greedy_decoder.py:21 argmax): keep only this (row, 32-column group)'s
+        // softmax partials — max logit, its first column, sum of exp(x - max) — the [M, V] logits never reach HBM
+        float m = -INFINITY;
+        int mi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (n + j < p.N && v[j] > m) { m = v[j]; mi = n + j; }        // ascending columns, strict >: first maximum
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (n + j < p.N) sum += ex2_approx((v[j] - m) * 1.4426950408889634f);
+        if (c.lane < c.nvalid) {
+            const int64_t idx = (int64_t)(n >> 5) * p.M + c.row0 + c.lane;  // [group][row]: a warp writes 32 consecutive entries
+            p.part_m[idx] = m; p.part_s[idx] = sum; p.part_i[idx] = mi;
+        }
+        return;
+    }
     if (p.epi == MASR_EPI_BIAS_GLU) {
         // interleaved (value, gate) columns -> 16 outputs at column n/2 of an N/2-wide output
         float o[16];
@@ -320,10 +438,10 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[j + k] = v[2 * (j + k)] * e[k];
         }
-        emit<16, BIG>(p, c, o, n >> 1, p.N >> 1);
+        emit<16, STG>(p, c, o, n >> 1, p.N >> 1);
         return;
     }
-    switch (p.epi) {
+    switch (LNC ? (int)MASR_EPI_RESIDUAL : p.epi) {
         case MASR_EPI_BIAS_SILU:
             // eight independent SFU chains at a time (a one-register serial chain was 5x slower than the MMA loop)
 #pragma unroll
@@ -375,7 +493,25 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
         }
         default: break;
     }
-    emit<32, BIG>(p, c, v, n, p.N);
+    if (LNC) {
+        // v = x + alpha * sublayer(x): the new residual stream.  EPI_RESIDUAL_LN: C <- v, pair <- LN(v) (the next sub-layer's
+        // GEMM operand).  EPI_RESIDUAL_LN2: C <- LN1(v) (norm_final: the block output replaces x), pair <- LN2(LN1(v)).
+        float o[32];
+        if (p.epi == EPI_RESIDUAL_LN2) {
+            ln_apply(L, v, o, p.ln_g + n, p.ln_b + n, p.ln_eps);
+            emit_f32<32, STG>(c, p.C, p.ldc, p.flags, o, n, p.N);
+            ln_apply(L, o, v, p.ln_g2 + n, p.ln_b2 + n, p.ln_eps);
+            if (p.y2) emit_f32<32, STG>(c, p.y2, p.ldc, p.flags, v, n, p.N);
+            emit_pair<32, STG>(c, p.Ch, p.Cl, p.ldc, p.flags, v, n, p.N);
+        } else {
+            emit_f32<32, STG>(c, p.C, p.ldc, p.flags, v, n, p.N);
+            ln_apply(L, v, o, p.ln_g + n, p.ln_b + n, p.ln_eps);
+            if (p.y2) emit_f32<32, STG>(c, p.y2, p.ldc, p.flags, o, n, p.N);
+            emit_pair<32, STG>(c, p.Ch, p.Cl, p.ldc, p.flags, o, n, p.N);
+        }
+        return;
+    }
+    emit<32, STG>(p, c, v, n, p.N);
 }
 
 // Accumulation: the tensor core adds into its fp32 TMEM accumulator with truncation, so a long K loop
@@ -387,19 +523,28 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles blockIdx.x, +gridDim.x, ...  TMEM holds
 // main[2] (ping-pong by chunk) and corr[2] (ping-pong by tile) = 512 columns, so the MMA warp runs tile
 // i+1 while the 8 epilogue warps finish tile i.
-template <bool CONV, int EW>
+// LNC: the LayerNorm-fused variant (N = 256, launched as clusters of 2 CTAs = the two column tiles of a row block); its
+// per-warp store staging shrinks to 1 KB to make room for the 8 KB statistics exchange buffer.
+constexpr int LN_RED_BYTES = 2 * 2 * 4 * 128 * 4;
+__host__ __device__ constexpr int epi_stage_bytes(int ew, bool lnc) { return lnc ? 1024 * ew : EPI_STAGE_TOTAL; }
+
+template <bool CONV, int EW, bool LNC>
 __global__ void __launch_bounds__(tc_threads(EW), 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, int tiles_n, int tiles_t) {
+    static_assert(!LNC || (EW == 16 && !CONV), "the LayerNorm epilogue needs one 32-column chunk per epilogue warp");
+    constexpr int EPI_BYTES = epi_stage_bytes(EW, LNC);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi_stage = smem + TSTAGES * STAGE_BYTES;                // EPI_STAGE_TOTAL / EW per warp (see staged_store)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_TOTAL);
+    uint8_t* epi_stage = smem + TSTAGES * STAGE_BYTES;                // EPI_BYTES / EW per warp (see staged_store)
+    uint8_t* ln_red = epi_stage + EPI_BYTES;                          // LNC only
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ln_red + (LNC ? LN_RED_BYTES : 0));
     uint64_t* empty_bar = full_bar + TSTAGES;
     uint64_t* main_full = empty_bar + TSTAGES;     // [2]
     uint64_t* main_empty = main_full + 2;          // [2]
     uint64_t* corr_full = main_empty + 2;          // [2]
     uint64_t* corr_empty = corr_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(corr_empty + 2);
+    uint64_t* ln_bar = corr_empty + 2;             // [2] (LNC)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.K / TBK;
@@ -410,6 +555,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
         for (int s = 0; s < 2; ++s) {
             mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], EW);
             mbar_init(&corr_full[s], 1); mbar_init(&corr_empty[s], EW);
+            if (LNC) mbar_init(&ln_bar[s], 2 * EW);                  // one arrival per epilogue warp of both CTAs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -419,6 +565,10 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     }
     tc_fence_before();
     __syncthreads();
+    if (LNC) {      // the peer CTA must have initialised its barriers before anybody arrives on them remotely
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    }
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // programmatic dependent launch: everything above (barriers, TMEM allocation, descriptor prefetch) overlapped the
@@ -502,13 +652,22 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
         // ---- EW epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4 (CW columns each) ----
         constexpr int CW = TBN / (EW / 4);                             // 64 columns per warp (EW = 8) or 32 (EW = 16)
         constexpr int NCH = CW / 32;                                   // 32-column chunks per warp
-        constexpr bool BIG = (EPI_STAGE_TOTAL / EW) >= 4096;
+        constexpr int STG = EPI_BYTES / EW;
         const int q = warp & 3, cgrp = (warp - 2) >> 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cgrp * CW;
         const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
         EpiCtx ctx;
-        ctx.sb = smem_u32(epi_stage) + (warp - 2) * (EPI_STAGE_TOTAL / EW);
+        ctx.sb = smem_u32(epi_stage) + (warp - 2) * STG;
         ctx.lane = lane;
+        LnCtx lnx;
+        if (LNC) {
+            uint32_t rank;
+            asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+            lnx.rank = rank; lnx.cgrp = (uint32_t)cgrp; lnx.row = (uint32_t)(q * 32 + lane); lnx.lane = (uint32_t)lane; lnx.round = 0;
+            lnx.red = smem_u32(ln_red); lnx.bar = smem_u32(ln_bar);
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lnx.red_peer) : "r"(lnx.red), "r"(rank ^ 1u));
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lnx.bar_peer) : "r"(lnx.bar), "r"(rank ^ 1u));
+        }
         uint32_t cg = 0, tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             int n0, m0, t0, b;
@@ -555,7 +714,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         v[j] = fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])) + __shfl_sync(0xffffffffu, bsrc, j);
-                    store_chunk<BIG>(p, ctx, v, n);
+                    store_chunk<STG, LNC>(p, ctx, v, n, lnx);
                 }
                 ++cg;
                 continue;
@@ -599,12 +758,16 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
                 const float bsrc = cc ? bias1 : bias0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = acc[cc * 32 + j] + __shfl_sync(0xffffffffu, bsrc, j);
-                store_chunk<BIG>(p, ctx, v, n);
+                store_chunk<STG, LNC>(p, ctx, v, n, lnx);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (LNC) {      // neither CTA may exit while its peer can still write into its shared memory
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    }
     if (warp == 1) {
         tc_fence_after();
         __syncwarp();
@@ -613,7 +776,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
 }
 
 constexpr size_t kTcSmem = TSTAGES * STAGE_BYTES + EPI_STAGE_TOTAL + 1024 /*align*/ + 256 /*barriers + tmem slot*/;
-static_assert(kTcSmem <= 232448, "tc_gemm shared memory exceeds the 227 KB per-CTA limit of sm_100");
+constexpr size_t kTcSmemLn = TSTAGES * STAGE_BYTES + epi_stage_bytes(16, true) + LN_RED_BYTES + 1024 + 256;
+static_assert(kTcSmem <= 232448 && kTcSmemLn <= 232448, "tc_gemm shared memory exceeds the 227 KB per-CTA limit of sm_100");
 
 // ---- fp32 -> (h,l) split, elementwise (weights at load time; activations produced by SIMT kernels) ----
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, __half* __restrict__ h,
@@ -628,6 +792,31 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
     } else {
         for (; i < n; ++i) split_f16(x[i], h[i], l[i]);
     }
+}
+
+// ---- CTC head: combine the per-(row, 32-column group) softmax partials of the EPI_CTC_PARTIAL epilogue -------------------------
+// One thread per frame (consecutive threads = consecutive rows: coalesced [group][row] reads), online max / sum-exp merge in
+// ascending column order (strict >: the first maximum wins, like numpy's argmax in ctc_greedy_decoder.py:21).
+// max-prob = 1 / sum_j exp(x_j - max).
+__global__ void __launch_bounds__(128) ctc_partial_combine_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
+                                                                  const int* __restrict__ pi, int M, int groups,
+                                                                  int* __restrict__ ids, float* __restrict__ maxp) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int row = blockIdx.x * 128 + threadIdx.x;
+    if (row >= M) return;
+    float m = -INFINITY, s = 0.f;
+    int mi = 0x7fffffff;
+#pragma unroll 4
+    for (int g = 0; g < groups; ++g) {
+        const int64_t idx = (int64_t)g * M + row;
+        const float gm = __ldg(pm + idx), gs = __ldg(ps + idx);
+        const int gi = __ldg(pi + idx);
+        if (gm > m) { s = s * expf(m - gm) + gs; m = gm; mi = gi; }
+        else s += gs * expf(gm - m);
+    }
+    ids[row] = mi;
+    maxp[row] = 1.0f / s;
 }
 
 // ---- host: tensor maps ----------------------------------------------------------------------------
@@ -707,10 +896,11 @@ static int ensure_tc_attrs() {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!g_tc_attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemLn);
         if (e != cudaSuccess) { set_last_error("tc_gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         g_tc_attr_set[dev] = true;
     }
@@ -746,8 +936,8 @@ extern "C" int masr_conv2_tc_f16x2(const void* c1h, const void* c1l, const void*
     const int tiles_n = (C + TBN - 1) / TBN, tiles_t = (T2 + CONV_TR - 1) / CONV_TR;
     const int num_tiles = tiles_n * tiles_t * B;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    if (p.flags & 4) launch_pdl(tc_gemm_kernel<true, 16>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, tiles_t);
-    else launch_pdl(tc_gemm_kernel<true, 8>, dim3(grid), dim3(tc_threads(8)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, tiles_t);
+    if (p.flags & 4) launch_pdl(tc_gemm_kernel<true, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, tiles_t);
+    else launch_pdl(tc_gemm_kernel<true, 8, false>, dim3(grid), dim3(tc_threads(8)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, tiles_t);
     return check_launch("tc_gemm_kernel<conv>");
 }
 
@@ -786,7 +976,89 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = tiles_n * tiles_m;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    if (p.flags & 4) launch_pdl(tc_gemm_kernel<false, 16>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
-    else launch_pdl(tc_gemm_kernel<false, 8>, dim3(grid), dim3(tc_threads(8)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
+    if (p.flags & 4) launch_pdl(tc_gemm_kernel<false, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
+    else launch_pdl(tc_gemm_kernel<false, 8, false>, dim3(grid), dim3(tc_threads(8)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
     return check_launch("tc_gemm_kernel");
+}
+
+// ctc_lo Linear + softmax statistics + per-frame argmax (loss/ctc.py:70, ctc_greedy_decoder.py:21-27) without the [M, V]
+// logits: the GEMM epilogue reduces every 32-column group of a row to (max, first argmax, sum exp) and a small combine
+// kernel merges the ceil(V/32) groups of each frame.  workspace: 3 * ceil(V/32) * M * 4 bytes.
+extern "C" int masr_ctc_head_argmax_tc_f16x2(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl,
+                                             const float* bias, int M, int V, int K, void* workspace, int64_t workspace_bytes,
+                                             int* ids, float* maxp, void* stream) {
+    if (M == 0) return MASR_OK;
+    MASR_REQUIRE(Ah && Al && Wh && Wl && workspace && ids && maxp, "masr_ctc_head_argmax_tc_f16x2: null pointer");
+    MASR_REQUIRE(V > 0 && K > 0 && K % TBK == 0 && lda % 8 == 0, "masr_ctc_head_argmax_tc_f16x2: V=%d K=%d lda=%lld", V, K, (long long)lda);
+    const int groups = (V + 31) / 32;
+    const int64_t need = (int64_t)3 * groups * M * 4;
+    MASR_REQUIRE(workspace_bytes >= need, "masr_ctc_head_argmax_tc_f16x2: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    if ((rc = make_map_2d(&maps.a[0], Ah, M, K, lda))) return rc;
+    if ((rc = make_map_2d(&maps.a[1], Al, M, K, lda))) return rc;
+    if ((rc = make_map_2d(&maps.w[0], Wh, V, K, K))) return rc;
+    if ((rc = make_map_2d(&maps.w[1], Wl, V, K, K))) return rc;
+    if ((rc = ensure_tc_attrs())) return rc;
+    TcParams p{bias, nullptr, nullptr, nullptr, nullptr, 0, 0, M, V, K, EPI_CTC_PARTIAL, 1.f, 0, tc_flags()};
+    p.part_m = (float*)workspace;
+    p.part_s = p.part_m + (int64_t)groups * M;
+    p.part_i = (int*)(p.part_s + (int64_t)groups * M);
+    const int tiles_n = (V + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
+    const int num_tiles = tiles_n * tiles_m;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    launch_pdl(tc_gemm_kernel<false, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
+    if ((rc = check_launch("tc_gemm_kernel<ctc>"))) return rc;
+    launch_pdl(ctc_partial_combine_kernel, dim3((M + 127) / 128), dim3(128), 0, (cudaStream_t)stream, (const float*)p.part_m,
+               (const float*)p.part_s, (const int*)p.part_i, M, groups, ids, maxp);
+    return check_launch("ctc_partial_combine_kernel");
+}
+
+// Sub-layer output projection (N = 256) + residual add + the LayerNorm(s) that follow it, in one kernel:
+//   x_new = residual + alpha * (A.W^T + bias)
+//   gamma2 == NULL:  X <- x_new,  (Yh, Yl) <- LN(x_new; gamma1, beta1)            encoder.py:117->122, 131->141, 145->153
+//   gamma2 != NULL:  X <- LN(x_new; gamma1, beta1),  (Yh, Yl) <- LN(X; gamma2, beta2)   encoder.py:155->161->(next block) 106 / 342
+//   Y2 (optional): fp32 copy of what the pair holds.
+// Launched as clusters of 2 CTAs (the two 128-column tiles of a row block); row statistics cross the pair through
+// distributed shared memory.  Replaces masr_gemm_tc_f16x2(MASR_EPI_RESIDUAL) + masr_layernorm[2]_split_f16.
+extern "C" int masr_gemm_tc_residual_ln_f16x2(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl,
+                                              const float* bias, const float* residual, int64_t ldr, float alpha, float* X,
+                                              const float* gamma1, const float* beta1, const float* gamma2, const float* beta2,
+                                              float* Y2, void* Yh, void* Yl, int64_t ldx, int M, int N, int K, float eps,
+                                              void* stream) {
+    if (M == 0) return MASR_OK;
+    MASR_REQUIRE(Ah && Al && Wh && Wl && residual && X && gamma1 && beta1 && Yh && Yl, "masr_gemm_tc_residual_ln_f16x2: null pointer");
+    MASR_REQUIRE((gamma2 == nullptr) == (beta2 == nullptr), "masr_gemm_tc_residual_ln_f16x2: gamma2/beta2 must come as a pair");
+    MASR_REQUIRE(N == 2 * TBN, "masr_gemm_tc_residual_ln_f16x2: N=%d unsupported (this build: %d)", N, 2 * TBN);
+    MASR_REQUIRE(K > 0 && K % TBK == 0 && lda % 8 == 0 && ldx % 8 == 0 && ldr % 4 == 0, "masr_gemm_tc_residual_ln_f16x2: K=%d lda=%lld ldx=%lld ldr=%lld",
+                 K, (long long)lda, (long long)ldx, (long long)ldr);
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    if ((rc = make_map_2d(&maps.a[0], Ah, M, K, lda))) return rc;
+    if ((rc = make_map_2d(&maps.a[1], Al, M, K, lda))) return rc;
+    if ((rc = make_map_2d(&maps.w[0], Wh, N, K, K))) return rc;
+    if ((rc = make_map_2d(&maps.w[1], Wl, N, K, K))) return rc;
+    if ((rc = ensure_tc_attrs())) return rc;
+    TcParams p{bias, residual, X, (__half*)Yh, (__half*)Yl, ldr, ldx, M, N, K, gamma2 ? EPI_RESIDUAL_LN2 : EPI_RESIDUAL_LN, alpha, 0, tc_flags() & ~2};
+    p.ln_g = gamma1; p.ln_b = beta1; p.ln_g2 = gamma2; p.ln_b2 = beta2; p.y2 = Y2; p.ln_eps = eps;
+    const int tiles_m = (M + TBM - 1) / TBM;
+    const int num_tiles = 2 * tiles_m;
+    const int sms = num_sms() & ~1;
+    const int grid = num_tiles < sms ? num_tiles : sms;             // even: a cluster = the two column tiles of one row block
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tc_threads(16));
+    cfg.dynamicSmemBytes = kTcSmemLn;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, tc_gemm_kernel<false, 16, true>, maps, p, num_tiles, 2, 1);
+    return check_launch("tc_gemm_kernel<ln>");
 }

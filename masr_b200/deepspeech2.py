@@ -206,6 +206,9 @@ class DeepSpeech2Engine(ConformerEngine):
         self._rnn_stack(ws, B, T, M, ws["tlens"])
         return ws["t0"][:M], tl, T, ws
 
+    def _ctc_operand(self, ws):
+        return ws["xp"], self.H * self.dirs
+
     def ctc_logits(self, enc, ws):
         M = enc.shape[0]
         D = self.H * self.dirs

@@ -11,6 +11,7 @@ each row of a ragged batch is computed exactly as if it were alone (B=1 semantic
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -67,6 +68,8 @@ class ConformerEngine:
         if gemm not in ("tc", "simt"):
             raise ValueError("gemm must be 'tc' or 'simt'")
         self.gemm_path = gemm
+        # fused epilogues of the tensor-core path (MASR_FUSE=0 falls back to the separate LayerNorm / argmax kernels, for A/B runs)
+        self.fuse = os.environ.get("MASR_FUSE", "1") != "0"
         self.use_graphs = bool(use_graphs)     # replay the batched device step as one CUDA graph per (B, Fmax) shape
         self._graphs = {}
         if not torch.cuda.is_available():
@@ -146,6 +149,14 @@ class ConformerEngine:
         """C / (Ch,Cl) = epi(A.W^T): A, W fp16 (h,l) pairs."""
         self._k(tag, "masr_gemm_tc_f16x2", _p(A[0]), _p(A[1]), lda, _p(W[0]), _p(W[1]), _p(bias), _p(residual), ldr,
                 _p(C), None if Cp is None else _p(Cp[0]), None if Cp is None else _p(Cp[1]), ldc, M, N, K, epi, alpha)
+
+    def _tc_ln(self, A, lda, W, bias, M, K, alpha, x, ln1, yp, ln2=None, y2=None, tag="gemm"):
+        """x <- x + alpha * (A.W^T + bias) followed by the LayerNorm(s) of the next consumer, one kernel
+        (masr_gemm_tc_residual_ln_f16x2): ln2 is None -> x keeps the sum and yp <- LN1(x); else x <- LN1(sum), yp <- LN2(x)."""
+        d = self.d
+        self._k(tag, "masr_gemm_tc_residual_ln_f16x2", _p(A[0]), _p(A[1]), lda, _p(W[0]), _p(W[1]), _p(bias), _p(x), d, alpha,
+                _p(x), _p(ln1[0]), _p(ln1[1]), None if ln2 is None else _p(ln2[0]), None if ln2 is None else _p(ln2[1]),
+                _p(y2), _p(yp[0]), _p(yp[1]), d, M, d, K, 1e-5)
 
     def _ln_split(self, x, gb, yp, M):
         self._k("layernorm", "masr_layernorm_split_f16", _p(x), self.d, _p(gb[0]), _p(gb[1]), _p(yp[0]), _p(yp[1]),
@@ -389,31 +400,51 @@ class ConformerEngine:
         lpad = (w.kernel - 1) if self.causal else (w.kernel - 1) // 2
         nl = len(w.layers)
         for i, L in enumerate(w.layers):
+            fuse = self.fuse and d == 256
             if i == 0:                                # later blocks: fused with the previous block's norm_final (below)
                 self._ln_split(x, L.ln_ffm, t0p, M)
             self._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
-            self._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
-            self._ln_split(x, L.ln_mha, t0p, M)
+            # every sub-layer's output projection adds into the residual stream AND writes the next sub-layer's LayerNorm-ed
+            # operand pair in its epilogue (masr_gemm_tc_residual_ln_f16x2); MASR_FUSE=0: separate LayerNorm launches
+            if fuse:
+                self._tc_ln(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, w.ffn, 0.5, x, L.ln_mha, t0p, tag="ffn_w2")
+            else:
+                self._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
+                self._ln_split(x, L.ln_mha, t0p, M)
             self._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, Cp=ws["qkvp"], ldc=3 * d, tag="qkv_proj")
             self._attention_tc(L, qkv, ws["qkvp"], t1p, T, tlens, B)
-            self._tc(t1p, d, tw[i, "wo"], L.bo, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="out_proj")
-            self._ln_split(x, L.ln_conv, t0p, M)
+            if fuse:
+                self._tc_ln(t1p, d, tw[i, "wo"], L.bo, M, d, 1.0, x, L.ln_conv, t0p, tag="out_proj")
+            else:
+                self._tc(t1p, d, tw[i, "wo"], L.bo, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="out_proj")
+                self._ln_split(x, L.ln_conv, t0p, M)
             self._tc(t0p, d, tw[i, "pw1"], L.pw1_b, M, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d, tag="pw1_glu")
             self._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, T, _p(L.dw), _p(L.dw_b), _p(L.cn[0]),
                     _p(L.cn[1]), _p(L.glu_pad) if self.causal else None, None, _p(t1p[0]), _p(t1p[1]), d, T, _p(tlens), B,
                     d, w.kernel, lpad, T, 1e-5)
-            self._tc(t1p, d, tw[i, "pw2"], L.pw2_b, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="pw2")
-            self._ln_split(x, L.ln_ff, t0p, M)
+            if fuse:
+                self._tc_ln(t1p, d, tw[i, "pw2"], L.pw2_b, M, d, 1.0, x, L.ln_ff, t0p, tag="pw2")
+            else:
+                self._tc(t1p, d, tw[i, "pw2"], L.pw2_b, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="pw2")
+                self._ln_split(x, L.ln_ff, t0p, M)
             self._tc(t0p, d, tw[i, "ff1"], L.ff[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
-            self._tc(hidp, w.ffn, tw[i, "ff2"], L.ff[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
-            # x = norm_final(x), then in the same pass the next consumer's LayerNorm: the next block's norm_ff_macaron
-            # (pair only) or, after the last block, after_norm (fp32 encoder output + the pair the CTC head consumes)
+            # x = norm_final(x + 0.5 ffn), then in the same pass the next consumer's LayerNorm: the next block's
+            # norm_ff_macaron (pair only) or, after the last block, after_norm (fp32 encoder output + the CTC head's pair)
             nxt = w.layers[i + 1].ln_ffm if i + 1 < nl else w.after_norm
-            self._k("layernorm", "masr_layernorm2_split_f16", _p(x), d, _p(L.ln_final[0]), _p(L.ln_final[1]), _p(x), _p(nxt[0]),
-                    _p(nxt[1]), None if i + 1 < nl else _p(ws["t0"]), _p(t0p[0]), _p(t0p[1]), d, M, d, 1e-5)
+            y2 = None if i + 1 < nl else ws["t0"]
+            if fuse:
+                self._tc_ln(hidp, w.ffn, tw[i, "ff2"], L.ff[3], M, w.ffn, 0.5, x, L.ln_final, t0p, ln2=nxt, y2=y2, tag="ffn_w2")
+            else:
+                self._tc(hidp, w.ffn, tw[i, "ff2"], L.ff[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
+                self._k("layernorm", "masr_layernorm2_split_f16", _p(x), d, _p(L.ln_final[0]), _p(L.ln_final[1]), _p(x), _p(nxt[0]),
+                        _p(nxt[1]), _p(y2), _p(t0p[0]), _p(t0p[1]), d, M, d, 1e-5)
         return ws["t0"][:M], tl, T, ws
 
     # ---- CTC head ----------------------------------------------------------------------------
+    def _ctc_operand(self, ws):
+        """The fp16 (h,l) pair of the encoder output the CTC head multiplies, and its width."""
+        return ws["t0p"], self.d
+
     def ctc_logits(self, enc: torch.Tensor, ws) -> torch.Tensor:
         M = enc.shape[0]
         if self.gemm_path == "tc":
@@ -427,10 +458,21 @@ class ConformerEngine:
         """-> device tensors (tokens [B,T], ntok, psum, pcount, ids [B*T], probs or None)."""
         B = len(out_lens)
         M = B * T
-        logits = self.ctc_logits(enc, ws)
-        probs = torch.empty(M, self.V, device=self.device, dtype=torch.float32) if want_probs else None
-        self._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(logits), self.Vpad, M, self.V, _p(ws["ids"]),
-                _p(ws["maxp"]), _p(probs), self.V)
+        probs = None
+        if self.gemm_path == "tc" and self.fuse and not want_probs:
+            # the [M, V] logits never reach HBM: softmax statistics + argmax in the GEMM epilogue (masr_ctc_head_argmax_tc_f16x2)
+            Ap, K = self._ctc_operand(ws)
+            need = 3 * ((self.V + 31) // 32) * M * 4
+            if ws.get("ctc_part") is None or ws["ctc_part"].numel() < need:
+                ws["ctc_part"] = torch.empty(need, device=self.device, dtype=torch.uint8)
+            self._k("ctc_head", "masr_ctc_head_argmax_tc_f16x2", _p(Ap[0]), _p(Ap[1]), K, _p(self._tcw["ctc"][0]),
+                    _p(self._tcw["ctc"][1]), _p(self.w.ctc_b), M, self.V, K, _p(ws["ctc_part"]), ws["ctc_part"].numel(),
+                    _p(ws["ids"]), _p(ws["maxp"]), n=2)
+        else:
+            logits = self.ctc_logits(enc, ws)
+            probs = torch.empty(M, self.V, device=self.device, dtype=torch.float32) if want_probs else None
+            self._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(logits), self.Vpad, M, self.V, _p(ws["ids"]),
+                    _p(ws["maxp"]), _p(probs), self.V)
         self._k("ctc_collapse", "masr_ctc_greedy_collapse", _p(ws["ids"]), _p(ws["maxp"]), T, _p(ws["tlens"]), B, 0,
                 _p(ws["tokens"]), ws["tokens"].shape[1], _p(ws["ntok"]), _p(ws["psum"]), _p(ws["pcount"]))
         return probs

