@@ -191,7 +191,6 @@ def test_ctc_head_fused_argmax(rt, M, V, K):
     torch.cuda.synchronize()
     assert torch.equal(ids0, ids1)
     ref = F.linear(A.double(), W.double(), b.double())
-    assert torch.equal(ids1.cpu().long(), torch.where(ref.argmax(1) == V - 1, torch.tensor(5), ref.argmax(1))) or True
     assert (ids1.cpu() == V - 1).sum() == 0 and (ids1.cpu() == 37).sum() == 0      # ties resolve to the first index
     assert (mp0 - mp1).abs().max().item() < 1e-6
     assert (mp1.cpu().double() - torch.softmax(ref, 1).max(1).values).abs().max().item() < 2e-5
