@@ -342,17 +342,34 @@ __device__ __forceinline__ void emit(const TcParams& p, const EpiCtx& c, const f
 // order — both CTAs obtain bit-identical statistics.  Two-pass (mean, then centred variance) like norm.cu; rounds alternate
 // between two buffers / two barriers, so a fast warp can never overwrite or complete a round that a slow one still reads.
 struct LnCtx {
-    uint32_t red, red_peer;      // shared::cta / shared::cluster byte addresses of red[2][2][4][128] floats
+    uint32_t red, red_peer;      // shared::cta / shared::cluster byte addresses of red[2][2][4][128] float2
     uint32_t bar, bar_peer;      // ... of the two mbarriers
     uint32_t rank, cgrp, row, lane;
     uint32_t round;
 };
 
-__device__ __forceinline__ float ln_exchange(LnCtx& L, float val) {
+// o = LayerNorm(v) * gamma + beta over the 256-wide row this thread holds 32 columns of (g, b: pointers to those columns).
+// ONE exchange per LayerNorm: every thread sends the mean and the centred sum of squares of its own 32 values (two-pass,
+// in registers); the 8 partials of a row are combined with the pairwise-update formula of Chan et al. (equal counts):
+//   mean = sum(m_i) / 8,   M2 = sum(M2_i) + 32 * sum((m_i - mean)^2),   var = M2 / 256
+// — as stable as the two-pass form of norm.cu.  Must be called BEFORE the thread's global stores of the tile: the
+// release.cluster arrive orders all earlier writes of the thread, and waiting for outstanding global stores there cost
+// several microseconds per exchange in the first version.
+__device__ __forceinline__ void ln_apply(LnCtx& L, const float (&v)[32], float (&o)[32], const float* g, const float* b, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) s += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+    const float m_loc = s * (1.0f / 32.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float a0 = v[j] - m_loc, a1 = v[j + 1] - m_loc, a2 = v[j + 2] - m_loc, a3 = v[j + 3] - m_loc;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
     const uint32_t buf = L.round & 1;
-    const uint32_t off = ((((buf * 2 + L.rank) * 4 + L.cgrp) * 128) + L.row) * 4;
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(L.red + off), "f"(val) : "memory");
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(L.red_peer + off), "f"(val) : "memory");
+    const uint32_t off = ((((buf * 2 + L.rank) * 4 + L.cgrp) * 128) + L.row) * 8;
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(L.red + off), "f"(m_loc), "f"(q) : "memory");
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(L.red_peer + off), "f"(m_loc), "f"(q) : "memory");
     __syncwarp();
     if (L.lane == 0) {
         asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(L.bar + buf * 8) : "memory");
@@ -368,30 +385,18 @@ __device__ __forceinline__ float ln_exchange(LnCtx& L, float val) {
         "bra LN_WAIT;\n\t"
         "LN_DONE:\n\t"
         "}" ::"r"(L.bar + buf * 8), "r"(parity) : "memory");
-    float tot = 0.f;
+    float pm[8], pq[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        float t;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(L.red + (((buf * 8 + k) * 128) + L.row) * 4) : "memory");
-        tot += t;
-    }
+    for (int k = 0; k < 8; ++k)      // fixed order: both CTAs obtain bit-identical statistics
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pm[k]), "=f"(pq[k]) : "r"(L.red + (((buf * 8 + k) * 128) + L.row) * 8) : "memory");
     ++L.round;
-    return tot;
-}
-
-// o = LayerNorm(v) * gamma + beta over the 256-wide row this thread holds 32 columns of (g, b: pointers to those columns)
-__device__ __forceinline__ void ln_apply(LnCtx& L, const float (&v)[32], float (&o)[32], const float* g, const float* b, float eps) {
-    float s = 0.f;
+    const float mean = (((pm[0] + pm[1]) + (pm[2] + pm[3])) + ((pm[4] + pm[5]) + (pm[6] + pm[7]))) * 0.125f;
+    float m2 = ((pq[0] + pq[1]) + (pq[2] + pq[3])) + ((pq[4] + pq[5]) + (pq[6] + pq[7]));
+    float dev2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) s += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-    const float mean = ln_exchange(L, s) * (1.0f / 256.0f);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        const float a0 = v[j] - mean, a1 = v[j + 1] - mean, a2 = v[j + 2] - mean, a3 = v[j + 3] - mean;
-        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-    }
-    const float rstd = rsqrtf(ln_exchange(L, q) * (1.0f / 256.0f) + eps);
+    for (int k = 0; k < 8; ++k) { const float dm = pm[k] - mean; dev2 += dm * dm; }
+    m2 = fmaf(32.0f, dev2, m2);
+    const float rstd = rsqrtf(m2 * (1.0f / 256.0f) + eps);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 gg = ldg_f4(g + j), bb = ldg_f4(b + j);          // warp-uniform addresses: one broadcast transaction
@@ -410,15 +415,23 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
     if (!LNC && p.epi == EPI_CTC_PARTIAL) {
         // CTC head (loss/ctc.py:70 softmax + ctc_greedy_decoder.py:21 argmax): keep only this (row, 32-column group)'s
         // softmax partials — max logit, its first column, sum of exp(x - max) — the [M, V] logits never reach HBM
-        float m = -INFINITY;
-        int mi = 0x7fffffff;
+        if (n + 31 >= p.N) {                                               // ragged last group (warp-uniform): mask once
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (n + j < p.N && v[j] > m) { m = v[j]; mi = n + j; }        // ascending columns, strict >: first maximum
+            for (int j = 0; j < 32; ++j)
+                if (n + j >= p.N) v[j] = -INFINITY;
+        }
+        float m = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+        int mj = 31;
+#pragma unroll
+        for (int j = 30; j >= 0; --j)
+            if (v[j] == m) mj = j;                                         // descending scan: the FIRST maximum wins
+        const int mi = n + mj;
+        const float mneg = -m * 1.4426950408889634f;
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (n + j < p.N) sum += ex2_approx((v[j] - m) * 1.4426950408889634f);
+        for (int j = 0; j < 32; ++j) sum += ex2_approx(fmaf(v[j], 1.4426950408889634f, mneg));   // exp(-inf) = 0 for masked columns
         if (c.lane < c.nvalid) {
             const int64_t idx = (int64_t)(n >> 5) * p.M + c.row0 + c.lane;  // [group][row]: a warp writes 32 consecutive entries
             p.part_m[idx] = m; p.part_s[idx] = sum; p.part_i[idx] = mi;
@@ -496,16 +509,16 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
     if (LNC) {
         // v = x + alpha * sublayer(x): the new residual stream.  EPI_RESIDUAL_LN: C <- v, pair <- LN(v) (the next sub-layer's
         // GEMM operand).  EPI_RESIDUAL_LN2: C <- LN1(v) (norm_final: the block output replaces x), pair <- LN2(LN1(v)).
+        // (all statistics exchanges come before the first global store of the tile, see ln_apply)
         float o[32];
+        ln_apply(L, v, o, p.ln_g + n, p.ln_b + n, p.ln_eps);
         if (p.epi == EPI_RESIDUAL_LN2) {
-            ln_apply(L, v, o, p.ln_g + n, p.ln_b + n, p.ln_eps);
-            emit_f32<32, STG>(c, p.C, p.ldc, p.flags, o, n, p.N);
             ln_apply(L, o, v, p.ln_g2 + n, p.ln_b2 + n, p.ln_eps);
+            emit_f32<32, STG>(c, p.C, p.ldc, p.flags, o, n, p.N);
             if (p.y2) emit_f32<32, STG>(c, p.y2, p.ldc, p.flags, v, n, p.N);
             emit_pair<32, STG>(c, p.Ch, p.Cl, p.ldc, p.flags, v, n, p.N);
         } else {
             emit_f32<32, STG>(c, p.C, p.ldc, p.flags, v, n, p.N);
-            ln_apply(L, v, o, p.ln_g + n, p.ln_b + n, p.ln_eps);
             if (p.y2) emit_f32<32, STG>(c, p.y2, p.ldc, p.flags, o, n, p.N);
             emit_pair<32, STG>(c, p.Ch, p.Cl, p.ldc, p.flags, o, n, p.N);
         }
@@ -525,7 +538,7 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
 // i+1 while the 8 epilogue warps finish tile i.
 // LNC: the LayerNorm-fused variant (N = 256, launched as clusters of 2 CTAs = the two column tiles of a row block); its
 // per-warp store staging shrinks to 1 KB to make room for the 8 KB statistics exchange buffer.
-constexpr int LN_RED_BYTES = 2 * 2 * 4 * 128 * 4;
+constexpr int LN_RED_BYTES = 2 * 2 * 4 * 128 * 8;     // red[buffer][source CTA][column group][row] (mean, M2)
 __host__ __device__ constexpr int epi_stage_bytes(int ew, bool lnc) { return lnc ? 1024 * ew : EPI_STAGE_TOTAL; }
 
 template <bool CONV, int EW, bool LNC>
@@ -565,10 +578,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     }
     tc_fence_before();
     __syncthreads();
-    if (LNC) {      // the peer CTA must have initialised its barriers before anybody arrives on them remotely
-        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-    }
+    // the peer CTA must have initialised its barriers before anybody arrives on them remotely: arrive here, wait (long
+    // since complete) right before the first exchange / after the producer and MMA loops
+    if (LNC) asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // programmatic dependent launch: everything above (barriers, TMEM allocation, descriptor prefetch) overlapped the
@@ -612,6 +624,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
                 }
             }
         }
+        if (LNC) asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
     } else if (warp == 1) {
         if (elect_one_sync()) {
             // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 @17, M>>4 @24
@@ -648,6 +661,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
                 umma_commit(&corr_full[tl & 1]);                       // whole tile (incl. corrections) complete
             }
         }
+        if (LNC) asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
     } else {
         // ---- EW epilogue warps: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4 (CW columns each) ----
         constexpr int CW = TBN / (EW / 4);                             // 64 columns per warp (EW = 8) or 32 (EW = 16)
@@ -667,6 +681,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             lnx.red = smem_u32(ln_red); lnx.bar = smem_u32(ln_bar);
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lnx.red_peer) : "r"(lnx.red), "r"(rank ^ 1u));
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lnx.bar_peer) : "r"(lnx.bar), "r"(rank ^ 1u));
+            asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
         }
         uint32_t cg = 0, tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
@@ -795,28 +810,45 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
 }
 
 // ---- CTC head: combine the per-(row, 32-column group) softmax partials of the EPI_CTC_PARTIAL epilogue -------------------------
-// One thread per frame (consecutive threads = consecutive rows: coalesced [group][row] reads), online max / sum-exp merge in
-// ascending column order (strict >: the first maximum wins, like numpy's argmax in ctc_greedy_decoder.py:21).
+// A CTA handles 32 frames: lane = frame (coalesced [group][row] reads), the 4 warps take interleaved quarters of the groups
+// (8 independent loads in flight per thread), online max / sum-exp merge per thread, then the four partials of a frame
+// are merged in ascending column order of their FIRST group... order only matters for ties: the candidate with the
+// larger max wins, equal maxima resolve to the lower column index (numpy's argmax, ctc_greedy_decoder.py:21).
 // max-prob = 1 / sum_j exp(x_j - max).
 __global__ void __launch_bounds__(128) ctc_partial_combine_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
                                                                   const int* __restrict__ pi, int M, int groups,
                                                                   int* __restrict__ ids, float* __restrict__ maxp) {
     pdl_wait();
     pdl_launch_dependents();
-    const int row = blockIdx.x * 128 + threadIdx.x;
-    if (row >= M) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + lane;
     float m = -INFINITY, s = 0.f;
     int mi = 0x7fffffff;
-#pragma unroll 4
-    for (int g = 0; g < groups; ++g) {
-        const int64_t idx = (int64_t)g * M + row;
-        const float gm = __ldg(pm + idx), gs = __ldg(ps + idx);
-        const int gi = __ldg(pi + idx);
-        if (gm > m) { s = s * expf(m - gm) + gs; m = gm; mi = gi; }
-        else s += gs * expf(gm - m);
+    if (row < M) {
+#pragma unroll 8
+        for (int g = w; g < groups; g += 4) {
+            const int64_t idx = (int64_t)g * M + row;
+            const float gm = __ldg(pm + idx), gs = __ldg(ps + idx);
+            const int gi = __ldg(pi + idx);
+            if (gm > m) { s = s * expf(m - gm) + gs; m = gm; mi = gi; }        // ascending groups within a thread: strict >
+            else s += gs * expf(gm - m);
+        }
     }
-    ids[row] = mi;
-    maxp[row] = 1.0f / s;
+    __shared__ float sm_[4][32], ss_[4][32];
+    __shared__ int si_[4][32];
+    sm_[w][lane] = m; ss_[w][lane] = s; si_[w][lane] = mi;
+    __syncthreads();
+    if (w == 0 && row < M) {
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            const float gm = sm_[k][lane], gs = ss_[k][lane];
+            const int gi = si_[k][lane];
+            if (gm > m || (gm == m && gi < mi)) { s = s * expf(m - gm) + gs; m = gm; mi = gi; }
+            else s += gs * expf(gm - m);
+        }
+        ids[row] = mi;
+        maxp[row] = 1.0f / s;
+    }
 }
 
 // ---- host: tensor maps ----------------------------------------------------------------------------
@@ -1010,7 +1042,7 @@ extern "C" int masr_ctc_head_argmax_tc_f16x2(const void* Ah, const void* Al, int
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     launch_pdl(tc_gemm_kernel<false, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
     if ((rc = check_launch("tc_gemm_kernel<ctc>"))) return rc;
-    launch_pdl(ctc_partial_combine_kernel, dim3((M + 127) / 128), dim3(128), 0, (cudaStream_t)stream, (const float*)p.part_m,
+    launch_pdl(ctc_partial_combine_kernel, dim3((M + 31) / 32), dim3(128), 0, (cudaStream_t)stream, (const float*)p.part_m,
                (const float*)p.part_s, (const int*)p.part_i, M, groups, ids, maxp);
     return check_launch("ctc_partial_combine_kernel");
 }

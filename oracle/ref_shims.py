@@ -73,3 +73,32 @@ def install():
         sys.path.insert(0, REFERENCE_ROOT)
     import masr  # noqa: F401  (the reference package)
     return masr
+
+
+def build_real_predictor(tmp: str, streaming: bool = True, wseed: int = 0, vocab_size: int = 4233):
+    """The unmodified reference's ``masr.predict.MASRPredictor`` (conformer.yml, ctc_greedy, CPU) over the synthetic weights
+    of ``masr_b200.synth`` — the same construction ``tests/golden/make_golden.py`` freezes its goldens from.  Used by
+    ``bench.py --impl reference`` when a reference tree is present (build container; never on the GPU box)."""
+    install()
+    import numpy as np
+    import torch
+    import yaml
+    from masr.model_utils.conformer.model import ConformerModel
+    from masr.predict import MASRPredictor
+    from masr_b200 import synth
+    cfg = yaml.safe_load(open(os.path.join(REFERENCE_ROOT, "configs", "conformer.yml"), encoding="utf-8"))
+    mi = os.path.join(tmp, f"mean_istd_{wseed}.json")
+    synth.write_mean_istd(mi, wseed)
+    model = ConformerModel(input_dim=80, vocab_size=vocab_size, mean_istd_path=mi, streaming=streaming,
+                           encoder_conf=cfg["encoder_conf"], decoder_conf=cfg["decoder_conf"], **cfg["model_conf"])
+    res = model.load_state_dict(synth.to_torch(synth.conformer_state_dict(wseed, vocab_size)), strict=False)
+    assert not res.unexpected_keys
+    mp = os.path.join(tmp, "inference.pt")
+    torch.jit.save(model.eval().export(), mp)
+    vp = os.path.join(tmp, "vocabulary.txt")
+    synth.write_vocabulary(vp, vocab_size)
+    cfg["dataset_conf"]["dataset_vocab"] = vp
+    cfg["dataset_conf"]["mean_istd_path"] = mi
+    cfg["decoder"] = "ctc_greedy"
+    np.random.seed(0)
+    return MASRPredictor(configs=cfg, model_path=mp, use_gpu=False)
