@@ -236,7 +236,34 @@ def main():
     T = 248
     gather_state = {}
 
-    resident = eng.prepare_resident(waves) if eng.use_graphs else None
+    def gather_pack(ws):
+        """The only collective of the path: every rank's packed outputs (token ids | counts | status | score sums: one int32
+        buffer, 33 KB) -> all ranks, one NCCL all_gather_into_tensor over NVLink.  Called INSIDE the CUDA-graph capture of the
+        device step (engine.graph_tail_hook), so a graph replay enqueues the whole step incl. the collective."""
+        pack = ws["out_pack"]
+        n = pack.numel()
+        buf = gather_state.get(("gbuf", n))
+        if buf is None:
+            buf = gather_state[("gbuf", n)] = torch.zeros(world * n, dtype=pack.dtype, device=pack.device)
+        dist.all_gather_into_tensor(buf, pack)
+        return buf
+
+    graph_gather = False
+    if world > 1:
+        dist.all_gather_into_tensor(torch.zeros(world * 8, dtype=torch.int32, device=dev), torch.zeros(8, dtype=torch.int32, device=dev))
+        torch.cuda.synchronize(dev)                  # communicator + channels are up before any capture
+        if eng.use_graphs and os.environ.get("MASR_GRAPH_GATHER", "1") != "0":
+            eng.graph_tail_hook = gather_pack
+            graph_gather = True
+    try:
+        resident = eng.prepare_resident(waves) if eng.use_graphs else None
+    except Exception as e:                            # NCCL refused the capture: fall back to an eager collective after the replay
+        if not graph_gather:
+            raise
+        sys.stderr.write(f"[bench] capturing the all-gather failed ({type(e).__name__}: {e}); eager collective instead\n")
+        eng.graph_tail_hook, graph_gather = None, False
+        eng._graphs.clear()
+        resident = eng.prepare_resident(waves)
 
     def device_step(eager=False, gather=True):
         """One pass of the hot path with inputs resident in HBM: fbank -> encoder -> CTC greedy
@@ -244,17 +271,32 @@ def main():
         by one (used for the per-kernel event timing of the roofline leg)."""
         if resident is not None and not eager:
             ws = resident()
+            if world > 1 and gather and not graph_gather:
+                gather_pack(ws)
         else:
+            hook, eng.graph_tail_hook = eng.graph_tail_hook, None
             feats, frames, status = eng.fbank(None, True, -20.0, wave_dev=wave_dev, offsets_dev=offs, lengths=lengths)
             enc, tl, Tm, ws = eng.encode(feats, frames)
             eng.ctc_greedy(enc, tl, Tm, ws)
-        if world > 1 and gather:
-            # the only collective of the path: gather token ids + counters of every rank's shard (NCCL over NVLink)
-            packed = torch.cat([ws["tokens"], ws["ntok"][:, None], ws["pcount"][:, None]], dim=1)
-            if "buf" not in gather_state or gather_state["buf"][0].shape != packed.shape:
-                gather_state["buf"] = [torch.empty_like(packed) for _ in range(world)]
-            dist.all_gather(gather_state["buf"], packed)
+            eng.graph_tail_hook = hook
+            if world > 1 and gather:
+                gather_pack(ws)
         return ws
+
+    def solo_tokens(ws_list):
+        """Token ids of a batch computed by THIS rank alone, eagerly (the captured step contains a collective)."""
+        ug, eng.use_graphs = eng.use_graphs, False
+        try:
+            return eng.transcribe(ws_list).tokens
+        finally:
+            eng.use_graphs = ug
+
+    def unpack(buf, r, B, Tt):
+        """rank r's slice of a gathered pack -> (token lists, counts)."""
+        n = B * Tt + 4 * B
+        on = buf[r * n:(r + 1) * n].cpu().numpy()
+        tok, ntok = on[:B * Tt].reshape(B, Tt), on[B * Tt:B * Tt + B]
+        return [tok[b, :ntok[b]].tolist() for b in range(B)]
 
     for _ in range(args.warmup):
         device_step()
@@ -285,6 +327,63 @@ def main():
 
     clocks = sampler.stop() if sampler else None      # clocks are sampled over the device-timed region only
 
+    # ---- the gathered result is checked on hardware: rank 0 recomputes OTHER ranks' shards and compares the token ids ----
+    gather_verified = None
+    strong = None
+    if world > 1:
+        ws = device_step()
+        torch.cuda.synchronize(dev)
+        Tt = ws["tokens"].shape[1]
+        gbuf = gather_state[("gbuf", ws["out_pack"].numel())]
+        if rank == 0:
+            ok = unpack(gbuf, 0, BATCH_PER_GPU, Tt) == solo_tokens(waves)
+            for r in sorted({1, world - 1}):
+                ok = ok and unpack(gbuf, r, BATCH_PER_GPU, Tt) == solo_tokens(make_waves(r))
+            gather_verified = bool(ok)
+        barrier()
+        # ---- strong scaling: ONE 32-utterance batch owned by rank 0, scattered over NCCL inside the timed
+        #      region (32/N utterances per GPU), decoded, gathered back; checked against rank 0's own full-batch result ----
+        if BATCH_PER_GPU % world == 0 and eng.use_graphs:
+            Bs = BATCH_PER_GPU // world
+            batch0 = make_waves(0)
+            full_tokens = solo_tokens(batch0) if rank == 0 else None
+            res_s = eng.prepare_resident(batch0[rank * Bs:(rank + 1) * Bs])
+            recv = res_s.g["wave"][:Bs * UTT_SAMPLES]
+            all_dev = torch.from_numpy(np.concatenate(batch0)).to(dev) if rank == 0 else None
+            chunks = list(all_dev.view(world, Bs * UTT_SAMPLES)) if rank == 0 else None
+
+            def strong_step():
+                dist.scatter(recv, scatter_list=chunks, src=0)
+                w_ = res_s()
+                if not graph_gather:
+                    gather_pack(w_)
+                return w_
+            for _ in range(3):
+                strong_step()
+            barrier()
+            sev = []
+            for _ in range(args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                w_ = strong_step()
+                e1.record()
+                sev.append((e0, e1))
+            barrier()
+            ms = sum(a.elapsed_time(b) for a, b in sev) / args.steps
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+            if rank == 0:
+                Tts = w_["tokens"].shape[1]
+                sbuf = gather_state[("gbuf", w_["out_pack"].numel())]
+                got = [t for r in range(world) for t in unpack(sbuf, r, Bs, Tts)]
+                strong = {"value": BATCH_PER_GPU * UTT_SAMPLES / SAMPLE_RATE / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms,
+                          "global_batch": BATCH_PER_GPU, "per_gpu_batch": Bs,
+                          "path": "rank 0 owns the batch in HBM -> NCCL scatter -> per-rank CUDA-graph step -> NCCL all-gather of the packed ids",
+                          "ids_match_single_gpu": bool(got == full_tokens)}
+            barrier()
+
     # ---- end to end through the public API: host float32 buffers in, token ids + score out --------------
     # (1) synchronous calls: predict_batch(batch) returns before the next batch is touched
     for _ in range(2):
@@ -302,6 +401,8 @@ def main():
     hook = None
     if world > 1:
         def hook(pack):
+            if graph_gather:
+                return                                # the all-gather is part of the captured step
             n = pack.numel()
             if gather_state.get("e2e_n") != n:
                 gather_state["e2e_buf"] = torch.empty(world * n, dtype=pack.dtype, device=pack.device)
@@ -388,6 +489,11 @@ def main():
                                       "api": "MASRPredictor.predict_batch(list) — one blocking call per batch"}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_time_shares": shares,
                 "cpu_baseline": cpu}
+        if world > 1:
+            line["gather_verified"] = gather_verified
+            line["config"]["collective"] = ("all_gather_into_tensor of the packed int32 outputs, captured in the step's CUDA graph"
+                                            if graph_gather else "all_gather_into_tensor of the packed int32 outputs after the graph replay")
+            line["strong_scaling"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

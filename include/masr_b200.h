@@ -295,6 +295,18 @@ int masr_ctc_prefix_beam(const int* cand_id, const float* cand_logp, const int* 
                          int B, int beam_size, int blank, float* pool, int* trie_parent, int* trie_tok, int64_t trie_cap,
                          int* out_tok, int64_t tok_stride, int* out_n, float* out_score, void* stream);
 
+/* Streaming form of masr_ctc_prefix_beam (beam_search_decoder.py:75-96: CTCBeamSearchDecoder.next() + decode(),
+ * reset_state()): the same search fed chunk by chunk.  lens[b] = frames of THIS chunk; resume = 0 starts a new utterance
+ * (reset_decoder), != 0 continues from state_i / state_f (sizes per utterance from masr_ctc_prefix_beam_state_size);
+ * trie_parent / trie_tok are sized for the whole stream (masr_ctc_prefix_beam_workspace with Tmax = its frame count) and
+ * persist between calls.  Outputs: the best prefix and its score after all frames seen so far — identical to one
+ * masr_ctc_prefix_beam call over the concatenated chunks. */
+int masr_ctc_prefix_beam_state_size(int64_t* ints_per_utt, int64_t* floats_per_utt);
+int masr_ctc_prefix_beam_stream(const int* cand_id, const float* cand_logp, const int* cand_cnt, int64_t bstride,
+                                const int* lens, int B, int beam_size, int blank, float* pool, int* trie_parent,
+                                int* trie_tok, int64_t trie_cap, int* state_i, float* state_f, int resume, int* out_tok,
+                                int64_t tok_stride, int* out_n, float* out_score, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
     const int* __restrict__ cand_id, const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int64_t bstride,
     const int* __restrict__ lens, int beam, int blank, float* __restrict__ pool_all, int* __restrict__ trie_parent,
     int* __restrict__ trie_tok, int64_t trie_cap, int* __restrict__ out_tok, int64_t tok_stride, int* __restrict__ out_n,
-    float* __restrict__ out_score) {
+    float* __restrict__ out_score, int* __restrict__ state_i, float* __restrict__ state_f, int resume) {
+    // state_i / state_f (optional, per utterance 3*BEAM_CAP+2 ints / 3*BEAM_CAP floats): the beam after the last frame, so the
+    // search can be resumed with the next chunk of frames (`resume` != 0) — CTCBeamSearchDecoder.next()/decode() of the
+    // reference's streaming path (beam_search_decoder.py:75-91); the trie and its hash persist in trie_parent / trie_tok.
     extern __shared__ __align__(16) uint8_t smem_beam[];
     BeamShared& S = *reinterpret_cast<BeamShared*>(smem_beam);
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -150,11 +153,22 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
     const int64_t node_cap = trie_cap / 5;
     const uint32_t hcap = (uint32_t)(trie_cap - node_cap);
     int* thash = tpar + node_cap;
-    for (int64_t i = tid; i < hcap; i += BEAM_THREADS) thash[i] = -1;
     int nbeam = 1, nnodes = 1;
-    if (tid == 0) {
-        S.node[0] = 0; S.par[0] = -1; S.last[0] = -1; S.pb[0] = 0.f; S.pnb[0] = -INFINITY; S.score[0] = 0.f;
-        tpar[0] = -1; ttok[0] = -1;
+    int* st_i = state_i ? state_i + (int64_t)b * (3 * BEAM_CAP + 2) : nullptr;
+    float* st_f = state_f ? state_f + (int64_t)b * (3 * BEAM_CAP) : nullptr;
+    if (resume && st_i) {
+        nbeam = st_i[3 * BEAM_CAP];
+        nnodes = st_i[3 * BEAM_CAP + 1];
+        if (tid < nbeam) {
+            S.node[tid] = st_i[tid]; S.par[tid] = st_i[BEAM_CAP + tid]; S.last[tid] = st_i[2 * BEAM_CAP + tid];
+            S.pb[tid] = st_f[tid]; S.pnb[tid] = st_f[BEAM_CAP + tid]; S.score[tid] = st_f[2 * BEAM_CAP + tid];
+        }
+    } else {
+        for (int64_t i = tid; i < hcap; i += BEAM_THREADS) thash[i] = -1;
+        if (tid == 0) {
+            S.node[0] = 0; S.par[0] = -1; S.last[0] = -1; S.pb[0] = 0.f; S.pnb[0] = -INFINITY; S.score[0] = 0.f;
+            tpar[0] = -1; ttok[0] = -1;
+        }
     }
     __syncthreads();
     for (int t = 0; t < T; ++t) {
@@ -351,6 +365,13 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
         __syncthreads();
         if (nbeam == 0) break;
     }
+    if (st_i) {
+        if (tid < nbeam) {
+            st_i[tid] = S.node[tid]; st_i[BEAM_CAP + tid] = S.par[tid]; st_i[2 * BEAM_CAP + tid] = S.last[tid];
+            st_f[tid] = S.pb[tid]; st_f[BEAM_CAP + tid] = S.pnb[tid]; st_f[2 * BEAM_CAP + tid] = S.score[tid];
+        }
+        if (tid == 0) { st_i[3 * BEAM_CAP] = nbeam; st_i[3 * BEAM_CAP + 1] = nnodes; }
+    }
     if (tid == 0) {
         int n = 0;
         float sc = -INFINITY;
@@ -408,6 +429,34 @@ extern "C" int masr_ctc_prefix_beam(const int* cand_id, const float* cand_logp, 
     }
     prefix_beam_kernel<<<B, BEAM_THREADS, sizeof(BeamShared), (cudaStream_t)stream>>>(
         cand_id, cand_logp, cand_cnt, bstride, lens, beam_size, blank, pool, trie_parent, trie_tok, trie_cap, out_tok, tok_stride,
-        out_n, out_score);
+        out_n, out_score, nullptr, nullptr, 0);
     return check_launch("prefix_beam_kernel");
+}
+
+extern "C" int masr_ctc_prefix_beam_state_size(int64_t* ints_per_utt, int64_t* floats_per_utt) {
+    MASR_REQUIRE(ints_per_utt && floats_per_utt, "masr_ctc_prefix_beam_state_size: null pointer");
+    *ints_per_utt = 3 * BEAM_CAP + 2;
+    *floats_per_utt = 3 * BEAM_CAP;
+    return MASR_OK;
+}
+
+// Streaming form (beam_search_decoder.py:75-96: CTCBeamSearchDecoder.next() + decode(), reset_state()): the same search
+// fed chunk by chunk.  `lens[b]` = frames of THIS chunk (0 = no new frames for that stream), `resume` = 0 starts a new
+// utterance (reset_decoder), != 0 continues from `state_*`; trie_parent / trie_tok must be sized for the whole stream
+// (masr_ctc_prefix_beam_workspace with Tmax = the longest stream in frames) and persist between calls.  Outputs = the best
+// prefix and its score after the frames seen so far — identical to one masr_ctc_prefix_beam call over the concatenation.
+extern "C" int masr_ctc_prefix_beam_stream(const int* cand_id, const float* cand_logp, const int* cand_cnt, int64_t bstride,
+                                           const int* lens, int B, int beam_size, int blank, float* pool, int* trie_parent,
+                                           int* trie_tok, int64_t trie_cap, int* state_i, float* state_f, int resume,
+                                           int* out_tok, int64_t tok_stride, int* out_n, float* out_score, void* stream) {
+    if (B == 0) return MASR_OK;
+    MASR_REQUIRE(cand_id && cand_logp && cand_cnt && lens && pool && trie_parent && trie_tok && out_tok && out_n && out_score &&
+                 state_i && state_f, "masr_ctc_prefix_beam_stream: null pointer");
+    MASR_REQUIRE(beam_size >= 1 && beam_size <= BEAM_CAP, "masr_ctc_prefix_beam_stream: beam_size=%d out of range (1..%d)", beam_size, BEAM_CAP);
+    cudaError_t e = cudaFuncSetAttribute(prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BeamShared));
+    if (e != cudaSuccess) { set_last_error("prefix_beam smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    prefix_beam_kernel<<<B, BEAM_THREADS, sizeof(BeamShared), (cudaStream_t)stream>>>(
+        cand_id, cand_logp, cand_cnt, bstride, lens, beam_size, blank, pool, trie_parent, trie_tok, trie_cap, out_tok, tok_stride,
+        out_n, out_score, state_i, state_f, resume);
+    return check_launch("prefix_beam_kernel<stream>");
 }

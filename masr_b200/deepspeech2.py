@@ -239,4 +239,5 @@ class DeepSpeech2Engine(ConformerEngine):
         probs = torch.empty(T, self.V, device=self.device, dtype=torch.float32) if want_probs else None
         self._k("ctc_argmax", "masr_ctc_frame_argmax_f32", _p(logits), self.Vpad, T, self.V, _p(ws["ids"]), _p(ws["maxp"]),
                 _p(probs), self.V)
+        st.last_logits = logits[:T]                    # (the streaming beam search reads the chunk's logits)
         return ws["ids"][:T], ws["maxp"][:T], probs

@@ -99,6 +99,7 @@ class ConformerEngine:
         self.d2h_bytes = 0
         self.last_gain = None
         self.prof: Optional[Dict[str, list]] = None      # tag -> [(start_event, end_event)], see profile()
+        self.graph_tail_hook = None                      # callable(ws) appended to the captured device step (see _graph_for)
         self._precompute_pos()
         self._tcw = {}
         if self.gemm_path == "tc":
@@ -565,6 +566,10 @@ class ConformerEngine:
                                           lengths=lengths, force_fmax=Fpad, status_out=ws0["status"])
             enc, tl, T, ws = self.encode(feats, frames, tlens_dev=g["tlens"])
             self.ctc_greedy(enc, tl, T, ws)
+            if self.graph_tail_hook is not None:
+                # e.g. the cross-rank gather of the packed outputs (NCCL all_gather_into_tensor) of a sharded deployment:
+                # captured into the same CUDA graph, so a replay is the whole device step incl. its one collective
+                self.graph_tail_hook(ws)
             return ws, status, T
 
         g["tlens"].fill_(subsampled_len(Fpad))
@@ -700,6 +705,7 @@ class ConformerEngine:
             g["graph"].replay()
             self.launches += g["launches"]
             return g["ws"]
+        step.g = g                                       # the static input buffers (a scatter may write g["wave"] directly)
         return step
 
     def _transcribe_graph(self, waves, use_db, target_db, return_frames) -> GreedyResult:
@@ -881,6 +887,7 @@ class ConformerEngine:
         st.cache_start += key_size - keep
         st.cache_len = keep
         st.offset += c
+        st.last_logits = ws["logits"][:c]              # (the streaming beam search reads the chunk's logits)
         return ws["ids"][:c], ws["maxp"][:c], probs
 
 
@@ -941,6 +948,62 @@ class ConformerStream:
             self.kv[i] = buf
         self.cap = new_cap
         self.cache_start = 0
+
+
+class StreamBeam:
+    """Streaming CTC prefix beam search of ONE stream on the GPU — ``BeamSearchDecoder.decode_chunk / reset_decoder``
+    (masr/decoders/beam_search_decoder.py:75-96, called at masr/predict.py:322,353): the beam, the prefix trie and its hash
+    stay on the device between chunks (masr_ctc_prefix_beam_stream), so after every chunk the best prefix equals the
+    whole-utterance search over all frames seen so far.  No language model (parity unpinned)."""
+
+    def __init__(self, eng: "ConformerEngine", beam_size: int = 300, cutoff_prob: float = 0.99, cutoff_top_n: int = 40,
+                 max_frames: int = 3000, max_chunk: int = 64):
+        self.eng, self.beam, self.cutoff, self.top_n = eng, int(beam_size), float(cutoff_prob), int(cutoff_top_n)
+        self.max_frames, self.max_chunk = int(max_frames), int(max_chunk)
+        dev, C = eng.device, _lib.C
+        pool_n, trie_n, si, sf = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        call("masr_ctc_prefix_beam_workspace", 1, self.max_frames, C.byref(pool_n), C.byref(trie_n))
+        call("masr_ctc_prefix_beam_state_size", C.byref(si), C.byref(sf))
+        i32, f32 = torch.int32, torch.float32
+        self.cand_id = torch.empty(self.max_chunk, 40, device=dev, dtype=i32)
+        self.cand_lp = torch.empty(self.max_chunk, 40, device=dev, dtype=f32)
+        self.cand_n = torch.empty(self.max_chunk, device=dev, dtype=i32)
+        self.pool = torch.empty(pool_n.value, device=dev, dtype=f32)
+        self.trie_par = torch.empty(trie_n.value, device=dev, dtype=i32)
+        self.trie_tok = torch.empty(trie_n.value, device=dev, dtype=i32)
+        self.trie_cap = trie_n.value
+        self.state_i = torch.zeros(si.value, device=dev, dtype=i32)
+        self.state_f = torch.zeros(sf.value, device=dev, dtype=f32)
+        self.lens = torch.zeros(1, device=dev, dtype=i32)
+        self.out_tok = torch.zeros(1, self.max_frames, device=dev, dtype=i32)
+        self.out = torch.zeros(2, device=dev, dtype=f32)             # [score, count (int32 bits)]
+        self.frames = 0
+
+    def reset(self):
+        """``reset_decoder`` (beam_search_decoder.py:93-96)."""
+        self.frames = 0
+
+    def push(self, logits: torch.Tensor, rows: int):
+        """CTC-head logits [>= rows, ld] of the new chunk's frames -> (token ids of the best prefix so far, its log score)."""
+        eng = self.eng
+        if rows > self.max_chunk:
+            raise ValueError(f"a chunk has at most {self.max_chunk} frames")
+        if self.frames + rows > self.max_frames:
+            raise AssertionError(f"stream longer than {self.max_frames} frames: create the StreamBeam with a larger max_frames")
+        if rows > 0:
+            eng._k("ctc_topk", "masr_ctc_topk_f32", _p(logits), logits.stride(0), rows, eng.V, self.top_n, self.cutoff,
+                   _p(self.cand_id), _p(self.cand_lp), _p(self.cand_n))
+        self.lens.fill_(rows)
+        n_view = self.out[1:2].view(torch.int32)
+        eng._k("prefix_beam", "masr_ctc_prefix_beam_stream", _p(self.cand_id), _p(self.cand_lp), _p(self.cand_n), self.max_chunk,
+               _p(self.lens), 1, self.beam, 0, _p(self.pool), _p(self.trie_par), _p(self.trie_tok), self.trie_cap, _p(self.state_i),
+               _p(self.state_f), 1 if self.frames else 0, _p(self.out_tok), self.out_tok.shape[1], _p(n_view), _p(self.out[0:1]))
+        self.frames += rows
+        oh = self.out.cpu()
+        n = int(oh[1:2].view(torch.int32).item())
+        toks = self.out_tok[0, :n].cpu().tolist() if n else []
+        eng.d2h_bytes += 8 + 4 * n
+        return toks, float(oh[0].item())
 
 
 def greedy_score(psum: np.float32, pcount: int) -> float:

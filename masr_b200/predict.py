@@ -97,7 +97,8 @@ class MASRPredictor:
         self._beam_conf = None
         if self.configs.decoder == 'ctc_beam_search':
             # GPU prefix beam search without a language model (the reference's external decoder + KenLM file are not
-            # available; alpha/beta/language_model_path are ignored).  Whole-utterance calls only; streaming stays greedy.
+            # available; alpha/beta/language_model_path are ignored): whole-utterance calls (engine.ctc_beam) and streaming
+            # (engine.StreamBeam = BeamSearchDecoder.decode_chunk / reset_decoder); both report the beam's log score.
             bc = dict(self.configs.get('ctc_beam_search_decoder_conf', {}) or {})
             self._beam_conf = {'beam_size': int(bc.get('beam_size', 300)), 'cutoff_prob': float(bc.get('cutoff_prob', 0.99)),
                                'cutoff_top_n': int(bc.get('cutoff_top_n', 40))}
@@ -122,6 +123,8 @@ class MASRPredictor:
         self._stream = self.predictor.new_stream() if (self.configs.streaming and self._can_stream) else None
         self._hist_ids: List[int] = []
         self._hist_probs: List[np.float32] = []
+        self._sbeam = None                                   # streaming beam-search state (created on the first chunk)
+        self._sbeam_result = ([], 0.0)
         # warm-up, as the reference does (predict.py:88-93)
         warmup_audio = np.random.uniform(low=-2.0, high=2.0, size=(134240,))
         self.predict(audio_data=warmup_audio, is_itn=False)
@@ -247,11 +250,23 @@ class MASRPredictor:
             if out is None:
                 continue
             ids, maxp, _ = out
+            if self._beam_conf is not None:
+                # predict.py:320-322: beam_search_decoder.decode_chunk on this chunk's posteriors (state kept on the device)
+                if self._sbeam is None:
+                    from .engine import StreamBeam
+                    self._sbeam = StreamBeam(eng, **self._beam_conf)
+                self._sbeam_result = self._sbeam.push(self._stream.last_logits, int(ids.shape[0]))
+                continue
             ids_h = ids.cpu().numpy()
             mp_h = maxp.cpu().numpy()
             self._hist_ids.extend(int(i) for i in ids_h)
             self._hist_probs.extend(mp_h[t] for t in range(len(ids_h)) if ids_h[t] != 0)
         self.cached_feat = self.cached_feat[end - CACHED_FEATURE_NUM:]
+        if self._beam_conf is not None:
+            toks, score = self._sbeam_result
+            if is_itn:
+                raise Exception("masr_b200: inverse text normalisation (is_itn) is outside the hot-path scope")
+            return {'text': ids_to_text(toks, self._text_featurizer.vocab_list), 'score': score}
         # greedy_decoder_chunk re-collapses the whole history (ctc_greedy_decoder.py:81-88)
         toks, prev = [], None
         for i in self._hist_ids:
@@ -277,6 +292,9 @@ class MASRPredictor:
         self.cached_feat = None
         self._hist_ids = []
         self._hist_probs = []
+        if self._sbeam is not None:                          # predict.py:352-353: beam_search_decoder.reset_decoder()
+            self._sbeam.reset()
+        self._sbeam_result = ([], 0.0)
 
 
 FRAME_SHIFT = 160

@@ -493,6 +493,7 @@ class PoolStream:
         self.batch[0, :n].copy_(feats_chunk)
         ids, maxp, tout = self.pool.step(self.batch, [n])
         probs = None if self.pool.probs is None else self.pool.probs[:tout[0]]
+        self.last_logits = self.pool.b["logits"][:tout[0]]      # (the streaming beam search reads the chunk's logits)
         return ids[0, :tout[0]], maxp[0, :tout[0]], probs
 
 

@@ -97,3 +97,119 @@ def test_gpu_beam_equals_restatement(seed, T, beam, topn, cut):
         got = otok[b, :on[b].item()].cpu().tolist()
         assert got == toks, (b, got, toks)
         assert abs(osc[b].item() - score) < 2e-3 * max(1.0, abs(score))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,T,beam,chunk", [(7, 75, 300, 16), (8, 50, 32, 7), (9, 33, 300, 33)])
+def test_gpu_streaming_beam_equals_one_shot(seed, T, beam, chunk):
+    """masr_ctc_prefix_beam_stream fed chunk by chunk (beam, trie and hash persist on the device) == one
+    masr_ctc_prefix_beam call over all frames: bit-identical tokens and score after every chunk boundary's prefix."""
+    import ctypes as C
+    from masr_b200 import _lib
+    _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    V = 4233
+    _, logits = rand_posteriors(seed, T, V)
+    ldl = (V + 15) // 16 * 16
+    L = torch.zeros(T, ldl, device=dev)
+    L[:, :V] = torch.from_numpy(logits).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    cid = torch.empty(T, 40, dtype=torch.int32, device=dev); clp = torch.empty(T, 40, device=dev)
+    cn = torch.empty(T, dtype=torch.int32, device=dev)
+    _lib.call("masr_ctc_topk_f32", L.data_ptr(), ldl, T, V, 40, 0.99, cid.data_ptr(), clp.data_ptr(), cn.data_ptr(), st)
+    pool_n, trie_n, si, sf = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    _lib.call("masr_ctc_prefix_beam_workspace", 1, T, C.byref(pool_n), C.byref(trie_n))
+    _lib.call("masr_ctc_prefix_beam_state_size", C.byref(si), C.byref(sf))
+
+    def bufs():
+        return (torch.empty(pool_n.value, device=dev), torch.empty(trie_n.value, dtype=torch.int32, device=dev),
+                torch.empty(trie_n.value, dtype=torch.int32, device=dev), torch.zeros(1, T, dtype=torch.int32, device=dev),
+                torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, device=dev))
+
+    def one_shot(n):
+        pool, tp, tt, otok, on, osc = bufs()
+        ld = torch.tensor([n], dtype=torch.int32, device=dev)
+        _lib.call("masr_ctc_prefix_beam", cid.data_ptr(), clp.data_ptr(), cn.data_ptr(), T, ld.data_ptr(), 1, beam, 0, pool.data_ptr(),
+                  tp.data_ptr(), tt.data_ptr(), trie_n.value, otok.data_ptr(), T, on.data_ptr(), osc.data_ptr(), st)
+        return otok[0, :on.item()].cpu().tolist(), osc.item()
+
+    pool, tp, tt, otok, on, osc = bufs()
+    sti = torch.zeros(si.value, dtype=torch.int32, device=dev); stf = torch.zeros(sf.value, device=dev)
+    done = 0
+    while done < T:
+        n = min(chunk, T - done)
+        ld = torch.tensor([n], dtype=torch.int32, device=dev)
+        _lib.call("masr_ctc_prefix_beam_stream", cid[done:].data_ptr(), clp[done:].data_ptr(), cn[done:].data_ptr(), T, ld.data_ptr(), 1,
+                  beam, 0, pool.data_ptr(), tp.data_ptr(), tt.data_ptr(), trie_n.value, sti.data_ptr(), stf.data_ptr(),
+                  1 if done else 0, otok.data_ptr(), T, on.data_ptr(), osc.data_ptr(), st)
+        done += n
+        want_t, want_s = one_shot(done)
+        assert otok[0, :on.item()].cpu().tolist() == want_t, done
+        assert osc.item() == want_s, done
+    # a chunk without frames returns the standing result; resume = 0 starts over
+    ld = torch.tensor([0], dtype=torch.int32, device=dev)
+    _lib.call("masr_ctc_prefix_beam_stream", cid.data_ptr(), clp.data_ptr(), cn.data_ptr(), T, ld.data_ptr(), 1, beam, 0, pool.data_ptr(),
+              tp.data_ptr(), tt.data_ptr(), trie_n.value, sti.data_ptr(), stf.data_ptr(), 1, otok.data_ptr(), T, on.data_ptr(), osc.data_ptr(), st)
+    assert (otok[0, :on.item()].cpu().tolist(), osc.item()) == one_shot(T)
+    ld = torch.tensor([min(chunk, T)], dtype=torch.int32, device=dev)
+    _lib.call("masr_ctc_prefix_beam_stream", cid.data_ptr(), clp.data_ptr(), cn.data_ptr(), T, ld.data_ptr(), 1, beam, 0, pool.data_ptr(),
+              tp.data_ptr(), tt.data_ptr(), trie_n.value, sti.data_ptr(), stf.data_ptr(), 0, otok.data_ptr(), T, on.data_ptr(), osc.data_ptr(), st)
+    assert (otok[0, :on.item()].cpu().tolist(), osc.item()) == one_shot(min(chunk, T))
+
+
+@pytest.mark.gpu
+def test_gpu_predict_stream_honours_ctc_beam_search(tmp_path):
+    """`decoder: ctc_beam_search` + predict_stream (predict.py:320-322,352-353): after every push the result is the prefix
+    beam search over all chunk posteriors so far — checked against the CPU restatement run on the engine's own chunk
+    posteriors (one-shot over their concatenation), push by push; reset_stream starts a fresh search."""
+    from conftest import make_audio, synth_weights
+    from masr_b200 import synth
+    from masr_b200.predict import MASRPredictor, chunk_starts, DECODING_WINDOW, CACHED_FEATURE_NUM
+    mp, vp = str(tmp_path / "m.pt"), str(tmp_path / "vocabulary.txt")
+    torch.save(synth.to_torch(synth_weights(0)), mp)
+    synth.write_vocabulary(vp)
+    base = {"use_model": "conformer", "streaming": True,
+            "preprocess_conf": {"feature_method": "fbank", "n_mels": 80, "sample_rate": 16000, "use_dB_normalization": True, "target_dB": -20},
+            "dataset_conf": {"dataset_vocab": vp}}
+    beam_conf = {"beam_size": 300, "cutoff_prob": 0.99, "cutoff_top_n": 40}
+    pred = MASRPredictor(configs={**base, "decoder": "ctc_beam_search", "ctc_beam_search_decoder_conf": beam_conf}, model_path=mp, use_gpu=True)
+    x = make_audio("speech", 77, 16000 * 3 + 2000)
+    pcm = (np.clip(x, -1, 1) * 32767).astype("<i2")
+    push = 8000
+    got = [pred.predict_stream(audio_data=pcm[s:s + push].tobytes(), is_end=s + push >= len(pcm)) for s in range(0, len(pcm), push)]
+    # the chunk posteriors of the same stream, from a second (greedy) predictor's engine, chunk by chunk
+    eng = pred.predictor
+    st = eng.new_stream()
+    vocab = synth.vocabulary()
+    remained, cached, probs_all, want = None, None, [], []
+    from masr_b200.audio import pcm_bytes_to_float32
+    for s in range(0, len(pcm), push):
+        is_end = s + push >= len(pcm)
+        new = pcm_bytes_to_float32(pcm[s:s + push].tobytes())
+        remained = new if remained is None else np.concatenate([remained, new])
+        feats, frames, _ = eng.fbank([remained])
+        gain = float(eng.last_gain.cpu().numpy()[0])
+        f = feats[0, :frames[0]]
+        cached = f if cached is None else torch.cat([cached, f], 0)
+        remained = (remained[160 * frames[0]:] * np.float32(gain)).astype(np.float32)
+        starts = chunk_starts(int(cached.shape[0]), is_end)
+        if not starts:
+            want.append(None)
+            continue
+        for cur in starts:
+            end = min(cur + DECODING_WINDOW, int(cached.shape[0]))
+            out = eng.encode_chunk(cached[cur:end], st, required_cache_size=-16, want_probs=True)
+            if out is not None:
+                probs_all.append(out[2].cpu().numpy())
+        cached = cached[end - CACHED_FEATURE_NUM:]
+        (score, toks), = obeam.prefix_beam_search(np.concatenate(probs_all), **beam_conf)
+        want.append({"text": "".join(vocab[i] for i in toks).replace("<space>", " "), "score": score})
+    assert len(got) == len(want) and any(w is not None and w["text"] for w in want)
+    for r, w in zip(got, want):
+        assert (r is None) == (w is None)
+        if r is not None:
+            assert r["text"] == w["text"], (r, w)
+            assert abs(r["score"] - w["score"]) < 5e-3 * max(1.0, abs(w["score"]))
+    pred.reset_stream()
+    again = [pred.predict_stream(audio_data=pcm[s:s + push].tobytes(), is_end=s + push >= len(pcm)) for s in range(0, len(pcm), push)]
+    assert again == got
