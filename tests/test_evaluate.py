@@ -29,7 +29,9 @@ def test_read_manifest(tmp_path):
 
 @pytest.mark.gpu
 def test_evaluate_loop_on_gpu(tmp_path):
-    """Labels = the path's own transcripts with one utterance perturbed: the mean CER is exactly that perturbation's share."""
+    """Labels = the CPU ORACLE's transcripts (fbank -> encoder -> greedy, the reference's B=1 loop) with one utterance
+    perturbed: the mean CER of the CUDA path over the manifest loop is exactly that perturbation's share, i.e. every GPU
+    transcript equals the oracle's (the earlier version compared the path with itself)."""
     import yaml
     from conftest import make_audio, synth_weights
     from masr_b200 import synth
@@ -42,8 +44,15 @@ def test_evaluate_loop_on_gpu(tmp_path):
            "dataset_conf": {"dataset_vocab": vp}}
     pred = MASRPredictor(configs=cfg, model_path=mp, use_gpu=True)
     audios = [make_audio("speech", 300 + i, 16000 * 2 + 777 * i) for i in range(7)]
-    texts = [pred.predict(audio_data=a.copy())["text"] for a in audios]
+    from oracle import conformer as oc, ctc as octc, fbank as ob
+    sd, vocab = synth.to_torch(synth_weights(0)), synth.vocabulary()
+    texts = []
+    with torch.no_grad():
+        for a in audios:
+            probs = oc.get_encoder_out(sd, oc.ConformerConfig(), torch.from_numpy(ob.featurize(a.copy()))[None])[0].numpy()
+            texts.append(octc.greedy_decode(probs, vocab)[1])
     assert all(len(t) > 1 for t in texts)
+    assert [pred.predict(audio_data=a.copy())["text"] for a in audios] == texts      # the single-utterance API agrees too
     labels = list(texts)
     labels[3] = labels[3][1:]                       # drop one character of one reference
     err, n = ev.evaluate(pred, zip(audios, labels), batch_size=3, metrics_type="cer")
