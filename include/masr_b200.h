@@ -249,6 +249,16 @@ int masr_lstm_step_f32(const float* gates_x, int64_t ldg, int64_t bstride, const
                        float* h_out_T, float* c_state, float* out, void* outh, void* outl, int64_t ld_out, int col_off,
                        const int* lens, int B, int H, int step, int reverse, void* stream);
 
+/* All T steps of one LSTM layer / direction in ONE persistent launch: every CTA keeps its slice of W_hh (the four gate rows
+ * of 8 hidden units) resident in shared memory, h_{t-1} is streamed through a shared-memory window and the steps are
+ * separated by a grid-wide barrier.  Same results as T calls of masr_lstm_step_f32 up to the order of the K summation.
+ * h0_T / hN_T: initial / final hidden state, transposed [ceil(B/32)][H][32]; c_state [B][H] updated in place; workspace
+ * from masr_lstm_seq_workspace_bytes.  H % 128 == 0, H <= 1024 (the shipped configs: 1024). */
+int masr_lstm_seq_workspace_bytes(int B, int H, int64_t* bytes);
+int masr_lstm_seq_f32(const float* gates_x, int64_t ldg, int64_t bstride, const float* Whh, const float* h0_T, float* hN_T,
+                      float* c_state, float* out, void* outh, void* outl, int64_t ld_out, int col_off, const int* lens, int B,
+                      int H, int T, int reverse, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- batched chunk (streaming) state ------------------------------------------------------------ */
 
 /* Append the chunk's new rows to every slot's cache (the `torch.cat` on time of the attention K|V cache, conformer/

@@ -69,9 +69,167 @@ __global__ void __launch_bounds__(LSTM_UNITS * 32) lstm_step_kernel(
     }
 }
 
+// ---- persistent form: the whole sequence of one layer / direction in ONE launch --------------------------------------------
+// The per-step kernel above re-reads W_hh (16 MB at H = 1024) from L2 on every step through a handful of warps and was pure
+// load latency (~70 us per step, 1240 launches per utterance batch).  Here every CTA keeps ITS slice of W_hh — the four gate
+// rows of LS_UNITS hidden units — resident in shared memory for all T steps (32 x H floats = 128 KB at H = 1024), streams
+// h_{t-1} ([H][32] per batch chunk, written by all CTAs in the previous step) through a double-buffered shared-memory window,
+// and the steps are separated by a grid-wide barrier (one atomic counter; the grid has at most one CTA per SM, all
+// co-resident).  Same arithmetic per output as lstm_step_kernel except the order of the K sum (two interleaved partial sums).
+constexpr int LS_UNITS = 8;       // hidden units per CTA (one warp each)
+constexpr int LS_KC = 128;        // rows of h staged per window
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(LS_UNITS * 32, 1) lstm_seq_kernel(
+    const float* __restrict__ gates_x, int64_t ldg, int64_t bstride, const float* __restrict__ Whh, const float* h0_T,
+    float* hN_T, float* __restrict__ c_state, float* __restrict__ out, __half* __restrict__ outh, __half* __restrict__ outl,
+    int64_t ld_out, int col_off, const int* __restrict__ lens, int B, int H, int T, int reverse, float* hbuf,
+    unsigned* counter) {
+    extern __shared__ __align__(16) float ls_smem[];
+    float* Ws = ls_smem;                              // [LS_UNITS][4][H]
+    float* hs = ls_smem + (size_t)LS_UNITS * 4 * H;   // [2][LS_KC][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int u0 = blockIdx.x * LS_UNITS, u = u0 + warp;
+    const int nb = (B + LSTM_BP - 1) / LSTM_BP;
+    const int64_t chunk_elems = (int64_t)H * LSTM_BP;
+    // resident weight slice: row (warp w, gate g) = Whh[g*H + u0 + w, :]
+    for (int r = 0; r < LS_UNITS * 4; ++r) {
+        const int w = r >> 2, g = r & 3;
+        const float* src = Whh + (int64_t)(g * H + u0 + w) * H;
+        for (int k = tid * 4; k < H; k += LS_UNITS * 32 * 4)
+            *reinterpret_cast<float4*>(Ws + (size_t)r * H + k) = ldg_f4(src + k);
+    }
+    __syncthreads();
+    const float* wrow = Ws + (size_t)warp * 4 * H;
+    const unsigned G = gridDim.x;
+    constexpr int PER = LS_KC * LSTM_BP / (LS_UNITS * 32 * 4);          // float4 per thread per window (= 4)
+    for (int s = 0; s < T; ++s) {
+        const float* hin = s == 0 ? h0_T : hbuf + (int64_t)((s - 1) & 1) * nb * chunk_elems;
+        float* hout = hbuf + (int64_t)(s & 1) * nb * chunk_elems;
+        for (int bc = 0; bc < nb; ++bc) {
+            const float* hT = hin + (int64_t)bc * chunk_elems;
+            float ai0 = 0.f, af0 = 0.f, ag0 = 0.f, ao0 = 0.f, ai1 = 0.f, af1 = 0.f, ag1 = 0.f, ao1 = 0.f;
+            // this lane's utterance: input gates, cell state and previous output are fetched now, consumed after the K loop
+            const int b = bc * LSTM_BP + lane;
+            const int len = b < B ? lens[b] : 0;
+            const bool active = s < len;
+            const int t = reverse ? len - 1 - s : s;
+            float gxi = 0.f, gxf = 0.f, gxg = 0.f, gxo = 0.f, c_prev = 0.f;
+            if (active) {
+                const float* gx = gates_x + ((int64_t)b * bstride + t) * ldg;
+                gxi = __ldg(gx + u); gxf = __ldg(gx + H + u); gxg = __ldg(gx + 2 * H + u); gxo = __ldg(gx + 3 * H + u);
+                c_prev = c_state[(int64_t)b * H + u];
+            }
+            const float h_prev = __ldcg(hT + (int64_t)u * LSTM_BP + lane);
+            float4 pre[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) pre[j] = __ldcg(reinterpret_cast<const float4*>(hT) + j * LS_UNITS * 32 + tid);
+            const int nwin = H / LS_KC;
+            for (int win = 0; win < nwin; ++win) {
+                float* hb = hs + (size_t)(win & 1) * LS_KC * LSTM_BP;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) *reinterpret_cast<float4*>(hb + (size_t)(j * LS_UNITS * 32 + tid) * 4) = pre[j];
+                __syncthreads();                           // window visible; the other buffer is free (read two windows ago)
+                if (win + 1 < nwin) {
+#pragma unroll
+                    for (int j = 0; j < PER; ++j)
+                        pre[j] = __ldcg(reinterpret_cast<const float4*>(hT + (size_t)(win + 1) * LS_KC * LSTM_BP) + j * LS_UNITS * 32 + tid);
+                }
+                const float* wk = wrow + win * LS_KC;
+#pragma unroll 4
+                for (int k = 0; k < LS_KC; k += 4) {
+                    const float4 wi = *reinterpret_cast<const float4*>(wk + k), wf = *reinterpret_cast<const float4*>(wk + H + k);
+                    const float4 wg = *reinterpret_cast<const float4*>(wk + 2 * H + k), wo = *reinterpret_cast<const float4*>(wk + 3 * H + k);
+                    const float h0 = hb[(k + 0) * LSTM_BP + lane], h1 = hb[(k + 1) * LSTM_BP + lane];
+                    const float h2 = hb[(k + 2) * LSTM_BP + lane], h3 = hb[(k + 3) * LSTM_BP + lane];
+                    ai0 = fmaf(wi.x, h0, ai0); ai1 = fmaf(wi.y, h1, ai1); ai0 = fmaf(wi.z, h2, ai0); ai1 = fmaf(wi.w, h3, ai1);
+                    af0 = fmaf(wf.x, h0, af0); af1 = fmaf(wf.y, h1, af1); af0 = fmaf(wf.z, h2, af0); af1 = fmaf(wf.w, h3, af1);
+                    ag0 = fmaf(wg.x, h0, ag0); ag1 = fmaf(wg.y, h1, ag1); ag0 = fmaf(wg.z, h2, ag0); ag1 = fmaf(wg.w, h3, ag1);
+                    ao0 = fmaf(wo.x, h0, ao0); ao1 = fmaf(wo.y, h1, ao1); ao0 = fmaf(wo.z, h2, ao0); ao1 = fmaf(wo.w, h3, ao1);
+                }
+            }
+            __syncthreads();                               // all warps are done with both windows before the next chunk refills them
+            float* hTo = hout + (int64_t)bc * chunk_elems + (int64_t)u * LSTM_BP + lane;
+            if (!active) {
+                *hTo = h_prev;                              // finished (or padding lane): state frozen
+            } else {
+                const float gi = sigmoid_f(gxi + (ai0 + ai1)), gf = sigmoid_f(gxf + (af0 + af1));
+                const float gg = tanhf(gxg + (ag0 + ag1)), go = sigmoid_f(gxo + (ao0 + ao1));
+                const float c = gf * c_prev + gi * gg;
+                const float h = go * tanhf(c);
+                c_state[(int64_t)b * H + u] = c;
+                *hTo = h;
+                const int64_t o = ((int64_t)b * bstride + t) * ld_out + col_off + u;
+                if (out) out[o] = h;
+                if (outh) {
+                    const __half hh = __float2half_rn(h);
+                    outh[o] = hh;
+                    outl[o] = __float2half_rn((h - __half2float(hh)) * 2048.0f);
+                }
+            }
+        }
+        // ---- grid-wide barrier: every CTA's h_t is in `hout` before anybody starts step s + 1 ----
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(counter, 1u);
+            const unsigned target = (unsigned)(s + 1) * G;
+            while (ld_acquire_u32(counter) < target) { }
+        }
+        __syncthreads();
+    }
+    // final state of this CTA's units -> hN_T (its own writes of the last step; T == 0 copies the initial state)
+    const float* hfin = T == 0 ? h0_T : hbuf + (int64_t)((T - 1) & 1) * nb * chunk_elems;
+    for (int bc = 0; bc < nb; ++bc)
+        hN_T[(int64_t)bc * chunk_elems + (int64_t)u * LSTM_BP + lane] = __ldcg(hfin + (int64_t)bc * chunk_elems + (int64_t)u * LSTM_BP + lane);
+}
+
 }  // namespace masr
 
 using namespace masr;
+
+extern "C" int masr_lstm_seq_workspace_bytes(int B, int H, int64_t* bytes) {
+    MASR_REQUIRE(bytes, "masr_lstm_seq_workspace_bytes: null pointer");
+    const int nb = (B + LSTM_BP - 1) / LSTM_BP;
+    *bytes = (int64_t)2 * nb * H * LSTM_BP * 4 + 256;      // two h buffers + the barrier counter
+    return MASR_OK;
+}
+
+// All T steps of one LSTM layer / direction in one persistent launch (same results as T calls of masr_lstm_step_f32 up to
+// the order of the K summation).  h0_T / hN_T: initial / final hidden state, transposed [ceil(B/32)][H][32] (may alias);
+// c_state [B][H] is updated in place; workspace from masr_lstm_seq_workspace_bytes.  H % 128 == 0, H <= 1024.
+extern "C" int masr_lstm_seq_f32(const float* gates_x, int64_t ldg, int64_t bstride, const float* Whh, const float* h0_T,
+                                 float* hN_T, float* c_state, float* out, void* outh, void* outl, int64_t ld_out, int col_off,
+                                 const int* lens, int B, int H, int T, int reverse, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+    if (B == 0) return MASR_OK;
+    MASR_REQUIRE(gates_x && Whh && h0_T && hN_T && c_state && lens && workspace && (out || (outh && outl)), "masr_lstm_seq_f32: null pointer");
+    MASR_REQUIRE(H % LS_KC == 0 && H % LS_UNITS == 0 && H <= 1024, "masr_lstm_seq_f32: H=%d unsupported (multiple of %d, <= 1024)", H, LS_KC);
+    int64_t need = 0;
+    masr_lstm_seq_workspace_bytes(B, H, &need);
+    MASR_REQUIRE(workspace_bytes >= need, "masr_lstm_seq_f32: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = H / LS_UNITS;
+    MASR_REQUIRE(grid <= sms, "masr_lstm_seq_f32: %d CTAs cannot be co-resident on %d SMs", grid, sms);
+    const size_t smem = ((size_t)LS_UNITS * 4 * H + 2 * LS_KC * LSTM_BP) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_last_error("lstm_seq smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    const int nb = (B + LSTM_BP - 1) / LSTM_BP;
+    float* hbuf = (float*)workspace;
+    unsigned* counter = (unsigned*)((char*)workspace + (int64_t)2 * nb * H * LSTM_BP * 4);
+    cudaMemsetAsync(counter, 0, sizeof(unsigned), (cudaStream_t)stream);
+    lstm_seq_kernel<<<grid, LS_UNITS * 32, smem, (cudaStream_t)stream>>>(gates_x, ldg, bstride, Whh, h0_T, hN_T, c_state, out,
+                                                                         (__half*)outh, (__half*)outl, ld_out, col_off, lens, B, H, T,
+                                                                         reverse, hbuf, counter);
+    return check_launch("lstm_seq_kernel");
+}
 
 extern "C" int masr_lstm_step_f32(const float* gates_x, int64_t ldg, int64_t bstride, const float* Whh, const float* h_in_T,
                                   float* h_out_T, float* c_state, float* out, void* outh, void* outl, int64_t ld_out,

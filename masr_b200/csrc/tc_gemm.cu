@@ -22,6 +22,7 @@
 //   Launched with programmatic dependent launch: the prologue overlaps the producer kernel's tail.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <math.h>
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -159,6 +160,7 @@ struct TcParams {
     float* part_m;
     float* part_s;
     int* part_i;
+    float inv_alpha;   // flags bit 4 (residual prefetch): 1 / alpha, exact (alpha is a power of two)
 };
 
 // internal epilogue codes (continuing include/masr_b200.h's MASR_EPI_*)
@@ -478,7 +480,10 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
             break;
         case MASR_EPI_RESIDUAL: {
             const bool vec_r = (p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
-            if (BIG && (p.flags & 2) && n + 31 < p.N && vec_r) {
+            if (p.flags & 16) {                               // the residual seeded the running sum (see the kernel): v = (r/alpha + A.W + bias)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+            } else if (BIG && (p.flags & 2) && n + 31 < p.N && vec_r) {
                 uint4 rr[8];
                 staged_load(c, rr, reinterpret_cast<const uint8_t*>(p.residual + c.row0 * p.ldr + n), p.ldr * 4);
 #pragma unroll
@@ -705,7 +710,13 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
                 ctx.row0 = (int64_t)m0 + q * 32;
                 ctx.nvalid = max(0, min(32, p.M - (m0 + q * 32)));
             }
-            if (nchunks == 1) {
+            // Residual epilogues (flags bit 4): this thread's residual values are fetched NOW, before the first accumulator
+            // is ready, and seed the running sum as residual / alpha (alpha is a power of two: exact), so the finished row is
+            // alpha * (sum + bias).  ncu r02: loaded after the last MMA, the row-strided residual read (8 x LDG.128 per
+            // thread, 32 lines per instruction) was more than half of the exposed epilogue of the single-tile-per-CTA GEMMs
+            // (w_2: ~11 of 34 us).
+            const bool pre_res = (LNC || p.epi == MASR_EPI_RESIDUAL) && (p.flags & 16);
+            if (nchunks == 1 && !pre_res) {
                 // K <= 256: main and correction accumulators complete together; go straight from TMEM to the
                 // stores 32 columns at a time (no 64-register running sum, so the activations keep their ILP)
                 mbar_wait(&main_full[cg & 1], (cg >> 1) & 1);
@@ -737,6 +748,25 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             float acc[CW];
 #pragma unroll
             for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+            if (pre_res && lane < ctx.nvalid) {
+#pragma unroll
+                for (int cc = 0; cc < NCH; ++cc) {
+                    const int n = nw + cc * 32;
+                    const float* r = p.residual + (ctx.row0 + lane) * p.ldr + n;
+                    if (n + 31 < p.N) {                                   // (host checked ldr % 4 == 0 and the 16-byte alignment)
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 rv = *reinterpret_cast<const float4*>(r + j);
+                            acc[cc * 32 + j] = rv.x * p.inv_alpha; acc[cc * 32 + j + 1] = rv.y * p.inv_alpha;
+                            acc[cc * 32 + j + 2] = rv.z * p.inv_alpha; acc[cc * 32 + j + 3] = rv.w * p.inv_alpha;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n + j < p.N) acc[cc * 32 + j] = r[j] * p.inv_alpha;
+                    }
+                }
+            }
             for (int c = 0; c < nchunks; ++c, ++cg) {
                 mbar_wait(&main_full[cg & 1], (cg >> 1) & 1);
                 tc_fence_after();
@@ -910,6 +940,16 @@ static int tc_flags() {
     return e ? atoi(e) : 5;
 }
 
+// flags bit 4: prefetch the residual into the running sum — needs alpha to be a power of two (so that r / alpha and the final
+// scaling are exact) and 16-byte aligned residual rows.  MASR_TC_PRERES=0 disables it.
+static int preres_flag(const float* residual, int64_t ldr, float alpha) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("MASR_TC_PRERES"); enabled = e ? atoi(e) != 0 : 1; }
+    int ex = 0;
+    const float mant = frexpf(alpha, &ex);
+    return (enabled && residual && mant == 0.5f && (ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0) ? 16 : 0;
+}
+
 static int num_sms() {
     static int n[64] = {0};
     int dev = 0;
@@ -1005,6 +1045,7 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     if ((rc = make_map_2d(&maps.w[1], Wl, N, K, K))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
     TcParams p{bias, residual, C, (__half*)Ch, (__half*)Cl, ldr, ldc, M, N, K, epilogue, alpha, 0, tc_flags()};
+    if (epilogue == MASR_EPI_RESIDUAL) { p.flags |= preres_flag(residual, ldr, alpha); p.inv_alpha = 1.0f / alpha; }
     const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = tiles_n * tiles_m;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
@@ -1075,6 +1116,7 @@ extern "C" int masr_gemm_tc_residual_ln_f16x2(const void* Ah, const void* Al, in
     if ((rc = ensure_tc_attrs())) return rc;
     TcParams p{bias, residual, X, (__half*)Yh, (__half*)Yl, ldr, ldx, M, N, K, gamma2 ? EPI_RESIDUAL_LN2 : EPI_RESIDUAL_LN, alpha, 0, tc_flags() & ~2};
     p.ln_g = gamma1; p.ln_b = beta1; p.ln_g2 = gamma2; p.ln_b2 = beta2; p.y2 = Y2; p.ln_eps = eps;
+    p.flags |= preres_flag(residual, ldr, alpha); p.inv_alpha = 1.0f / alpha;
     const int tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = 2 * tiles_m;
     const int sms = num_sms() & ~1;

@@ -6,6 +6,7 @@ recurrence run on the fp32 FMA pipe, one launch per time step (replayed as a CUD
 the chunked streaming path with carried (h, c) state (inference_predictor.py:66-78) are both implemented."""
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -101,6 +102,8 @@ class DeepSpeech2Engine(ConformerEngine):
         super().__init__(weights_src, streaming, device, max_len, gemm, use_graphs)
         self.H = self.w.hidden
         self.dirs = self.w.dirs
+        # one persistent launch per layer and direction (masr_lstm_seq_f32) instead of one launch per time step
+        self.persistent_lstm = os.environ.get("MASR_LSTM_PERSISTENT", "1") != "0"
         if bool(streaming) != (self.dirs == 1):
             raise Exception("streaming DeepSpeech2 needs forward-only LSTM weights, non-streaming bidirectional ones")
 
@@ -169,10 +172,20 @@ class DeepSpeech2Engine(ConformerEngine):
                     cur = 0
                 else:
                     hT, c, cur = stream.hT[l].unsqueeze(1), stream.c[l], stream.cur[l]
-                for s in range(T):
-                    self._k("lstm_step", "masr_lstm_step_f32", _p(gx), 4 * H, T, _p(ent["whh"][di]), _p(hT[cur]), _p(hT[1 - cur]),
-                            _p(c), _p(out), None, None, D, di * H, _p(tlens), B, H, s, di)
+                if self.persistent_lstm and H % 128 == 0 and H <= 1024:
+                    # the whole recurrence of this layer / direction in one persistent launch (W_hh slices resident in shared memory)
+                    if ws.get("lstm_ws") is None:
+                        nbytes = _lib.C.c_int64(0)
+                        call("masr_lstm_seq_workspace_bytes", B, H, _lib.C.byref(nbytes))
+                        ws["lstm_ws"] = torch.empty(nbytes.value, device=self.device, dtype=torch.uint8)
+                    self._k("lstm_seq", "masr_lstm_seq_f32", _p(gx), 4 * H, T, _p(ent["whh"][di]), _p(hT[cur]), _p(hT[1 - cur]), _p(c),
+                            _p(out), None, None, D, di * H, _p(tlens), B, H, T, di, _p(ws["lstm_ws"]), ws["lstm_ws"].numel())
                     cur = 1 - cur
+                else:
+                    for s in range(T):
+                        self._k("lstm_step", "masr_lstm_step_f32", _p(gx), 4 * H, T, _p(ent["whh"][di]), _p(hT[cur]), _p(hT[1 - cur]),
+                                _p(c), _p(out), None, None, D, di * H, _p(tlens), B, H, s, di)
+                        cur = 1 - cur
                 if stream is not None:
                     stream.cur[l] = cur
             self._k("layernorm", "masr_layernorm_split_f16", _p(out), D, _p(ent["ln"][0]), _p(ent["ln"][1]), _p(xp[0]), _p(xp[1]),

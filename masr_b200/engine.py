@@ -68,8 +68,12 @@ class ConformerEngine:
         if gemm not in ("tc", "simt"):
             raise ValueError("gemm must be 'tc' or 'simt'")
         self.gemm_path = gemm
-        # fused epilogues of the tensor-core path (MASR_FUSE=0 falls back to the separate LayerNorm / argmax kernels, for A/B runs)
-        self.fuse = os.environ.get("MASR_FUSE", "1") != "0"
+        # fused epilogues of the tensor-core path.  CTC head (softmax partials + argmax in the GEMM epilogue, no [M,V] logits):
+        # on (MASR_FUSE_CTC=0 for A/B runs).  LayerNorm behind the residual projections (cluster of 2 CTAs + DSMEM): measured
+        # r02 NOT faster than the separate LayerNorm launch — with one tile per CTA the longer epilogue is fully exposed
+        # (w_2 34.3 -> 42.6 us vs 6.0 us for the LayerNorm kernel, profiles/r02_ln_fusion.md) — so off unless MASR_FUSE_LN=1.
+        self.fuse_ctc = os.environ.get("MASR_FUSE_CTC", "1") != "0"
+        self.fuse = os.environ.get("MASR_FUSE_LN", "0") == "1"
         self.use_graphs = bool(use_graphs)     # replay the batched device step as one CUDA graph per (B, Fmax) shape
         self._graphs = {}
         if not torch.cuda.is_available():
@@ -460,7 +464,7 @@ class ConformerEngine:
         B = len(out_lens)
         M = B * T
         probs = None
-        if self.gemm_path == "tc" and self.fuse and not want_probs:
+        if self.gemm_path == "tc" and self.fuse_ctc and not want_probs:
             # the [M, V] logits never reach HBM: softmax statistics + argmax in the GEMM epilogue (masr_ctc_head_argmax_tc_f16x2)
             Ap, K = self._ctc_operand(ws)
             need = 3 * ((self.V + 31) // 32) * M * 4

@@ -48,10 +48,22 @@ for k in range(args.warm + args.pushes):
     if k >= args.warm:
         lat.append((time.perf_counter() - t0) * 1e3)
 wall = time.perf_counter() - t_start
+# correctness on a sample (the stream lines carried no check): the same PCM of a few streams through a fresh
+# ONE-slot pool (= the single-stream predict_stream path the parity tests pin to the reference goldens) must give the same text
+verified = {}
+texts = {s: (out[s] or {}).get("text", "") for s in range(S)}
+for s in sorted({0, S // 2, S - 1}):
+    solo = StreamPool(eng, synth.vocabulary(), n_slots=1, max_frames=((total // 160) // 4 + 64))
+    r = None
+    for k in range(args.warm + args.pushes):
+        r = solo.push({0: pcm[s][k * PUSH:(k + 1) * PUSH].tobytes()}, is_end=False)[0] or r
+    verified[s] = bool(r is not None and r["text"] == texts[s] and len(r["text"]) > 0)
+assert all(verified.values()), verified
 audio = S * args.pushes * PUSH / 16000.0
 lat = np.asarray(lat)
 print(json.dumps({"config": f"{args.model} streaming, {S} live streams x {args.pushes} pushes of 0.5 s, predict_stream semantics, ctc_greedy",
                   "audio_seconds_per_second": audio / wall, "push_latency_ms": {"mean": float(lat.mean()), "p50": float(np.median(lat)),
                                                                                 "p95": float(np.percentile(lat, 95)), "max": float(lat.max())},
                   "real_time_factor_per_stream": (wall / args.pushes) / 0.5, "kernel_launches_per_push": (eng.launches - l0) / args.pushes,
-                  "sample_text_len": len(next(v for v in out.values() if v is not None)["text"]) if any(v is not None for v in out.values()) else 0}))
+                  "sample_text_len": len(next(v for v in out.values() if v is not None)["text"]) if any(v is not None for v in out.values()) else 0,
+                  "streams_equal_single_stream_path": {str(k): v for k, v in verified.items()}}))
