@@ -203,9 +203,40 @@ class MASRPredictor:
             # AudioSegment.normalize raises ValueError when gain > max_gain_db (audio.py:301-303)
             raise ValueError("无法将段规范化到目标dB，音频增益已经超过max_gain_db (300.0dB)")
 
-    def predict_long(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000):
-        raise NotImplementedError("predict_long needs the VAD model (masr/infer_utils/vad_predictor.py), which is "
-                                  "outside the hot-path scope (SURVEY.md §8f4)")
+    def init_vad(self, vad_predictor=None, vad_model_path=None):
+        """predict.py:139-142.  ``vad_predictor``: any object with the reference's ``get_speech_timestamps(samples,
+        sampling_rate)``; else the silero ONNX model at ``vad_model_path`` through onnxruntime (masr_b200.vad.SileroVAD)."""
+        if vad_predictor is not None:
+            self.vad_predictor = vad_predictor
+        elif getattr(self, "vad_predictor", None) is None:
+            if vad_model_path is None:
+                raise Exception("masr_b200: predict_long needs a VAD: pass vad_predictor=... (an object with "
+                                "get_speech_timestamps) or vad_model_path=<silero_vad.onnx> (needs onnxruntime)")
+            from .vad import SileroVAD
+            self.vad_predictor = SileroVAD(vad_model_path)
+
+    def predict_long(self, audio_data, use_pun=False, is_itn=False, sample_rate=16000, vad_predictor=None, vad_model_path=None):
+        """Long-form recognition (predict.py:195-234): VAD segments -> recognise -> join with '，' and average the scores.
+        All segments of the recording go through ONE batched GPU pass (``predict_batch``) instead of the reference's
+        one-``predict``-per-segment loop; each segment's result equals ``predict(segment)`` (B=1 semantics)."""
+        self.init_vad(vad_predictor, vad_model_path)
+        samples, sr = load_audio(audio_data, sample_rate)
+        self._check_rate(sr)
+        stamps = self.vad_predictor.get_speech_timestamps(samples, sr)
+        segs = [samples[t['start']:t['end']] for t in stamps]
+        results = self.predict_batch(segs, sample_rate=sr) if segs else []
+        texts, scores = '', []
+        for r in results:
+            if r['text'] != '':
+                texts = texts + r['text'] if use_pun else texts + '，' + r['text']
+            scores.append(r['score'])
+        if texts[:1] == '，':
+            texts = texts[1:]
+        if use_pun and len(texts) > 0:
+            logger.warning('标点符号模型没有初始化！')
+        if is_itn:
+            raise Exception("masr_b200: inverse text normalisation (is_itn) is outside the hot-path scope")
+        return {'text': texts, 'score': round(sum(scores) / len(scores), 2) if scores else 0}
 
     # ---------------------------------------------------------------------------------------------
     def predict_stream(self, audio_data, is_end=False, use_pun=False, is_itn=False, channels=1, samp_width=2,

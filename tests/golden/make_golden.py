@@ -400,11 +400,58 @@ def gen_predictor_deepspeech2(tmp):
     print("pushes", pushes)
 
 
+def vad_prob_cases():
+    """Deterministic per-window speech-probability tracks (what the silero network would emit) exercising every branch of
+    the segmentation state machine: short blips (< min speech), short dips (< min silence), adjacent segments closer than
+    two pads, speech running to the end of the audio, an empty track."""
+    rng = np.random.default_rng(7)
+    cases = []
+    for k in range(6):
+        n = int(rng.integers(40, 400))
+        p = np.clip(rng.normal(0.2, 0.1, n), 0, 1)
+        pos = 0
+        while pos < n:
+            gap, run = int(rng.integers(1, 40)), int(rng.integers(1, 60))
+            pos += gap
+            p[pos:pos + run] = np.clip(rng.normal(0.85, 0.1, max(0, min(n, pos + run) - pos)), 0, 1)
+            pos += run
+        if k == 1:
+            p[-30:] = 0.9                                  # speech until the end
+        if k == 2:
+            p[:] = 0.1                                     # no speech at all
+        tail = int(rng.integers(0, 512))
+        cases.append({"probs": [float(np.float32(v)) for v in p], "samples": (n - 1) * 512 + (tail or 512)})
+    return cases
+
+
+def gen_vad():
+    """``VADPredictor.get_speech_timestamps`` (vad_predictor.py:106-175) with the ONNX network replaced by a scripted
+    probability track: freezes the segmentation state machine of predict_long."""
+    import types
+    sys.modules.setdefault("onnxruntime", types.ModuleType("onnxruntime"))
+    from masr.infer_utils.vad_predictor import VADPredictor
+    out = []
+    for case in vad_prob_cases():
+        for kw in ({}, {"threshold": 0.6, "min_speech_duration_ms": 100, "min_silence_duration_ms": 300, "speech_pad_ms": 100}):
+            v = object.__new__(VADPredictor)
+            v.threshold, v.min_speech_duration_ms = kw.get("threshold", 0.5), kw.get("min_speech_duration_ms", 250)
+            v.min_silence_duration_ms, v.window_size_samples = kw.get("min_silence_duration_ms", 100), 512
+            v.speech_pad_ms = kw.get("speech_pad_ms", 30)
+            it = iter(case["probs"])
+            VADPredictor.reset_states(v)
+            v.__class__ = type("ScriptedVAD", (VADPredictor,), {"__call__": lambda self, x, sr, it=it: np.float32(next(it))})
+            ts = v.get_speech_timestamps(np.zeros(case["samples"], np.float32), 16000)
+            out.append({"probs": case["probs"], "samples": case["samples"], "kw": kw, "timestamps": ts})
+    with open(os.path.join(HERE, "vad_timestamps_golden.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f)
+    print("vad cases", [(len(c["probs"]), len(c["timestamps"])) for c in out])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     with tempfile.TemporaryDirectory() as tmp:
         which = sys.argv[1:] or ["fbank", "encoder", "predictor", "efficient", "squeezeformer", "deepspeech2",
-                                  "predictor_squeezeformer", "predictor_efficient", "predictor_deepspeech2"]
+                                  "predictor_squeezeformer", "predictor_efficient", "predictor_deepspeech2", "vad"]
         if "deepspeech2" in which:
             gen_deepspeech2(tmp)
         if "squeezeformer" in which:
@@ -423,3 +470,5 @@ if __name__ == "__main__":
             gen_predictor_deepspeech2(tmp)
         if "efficient" in which:
             gen_efficient(tmp)
+        if "vad" in which:
+            gen_vad()

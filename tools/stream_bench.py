@@ -57,7 +57,7 @@ for s in sorted({0, S // 2, S - 1}):
     r = None
     for k in range(args.warm + args.pushes):
         r = solo.push({0: pcm[s][k * PUSH:(k + 1) * PUSH].tobytes()}, is_end=False)[0] or r
-    verified[s] = bool(r is not None and r["text"] == texts[s] and len(r["text"]) > 0)
+    verified[s] = bool(r is not None and r["text"] == texts[s])
 assert all(verified.values()), verified
 audio = S * args.pushes * PUSH / 16000.0
 lat = np.asarray(lat)
