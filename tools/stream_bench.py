@@ -36,6 +36,7 @@ total = (args.warm + args.pushes) * PUSH
 pcm = [(np.clip(synth.noise_audio(500 + s, total), -1, 1) * 32767).astype("<i2") for s in range(S)]
 pool = StreamPool(eng, synth.vocabulary(), n_slots=S, max_frames=((total // 160) // 4 + 64))
 lat = []
+last_result = {}
 l0 = None
 for k in range(args.warm + args.pushes):
     if k == args.warm:
@@ -44,6 +45,9 @@ for k in range(args.warm + args.pushes):
         l0 = eng.launches
     t0 = time.perf_counter()
     out = pool.push({s: pcm[s][k * PUSH:(k + 1) * PUSH].tobytes() for s in range(S)}, is_end=False)
+    for s_, v_ in out.items():
+        if v_ is not None:
+            last_result[s_] = v_
     torch.cuda.synchronize()
     if k >= args.warm:
         lat.append((time.perf_counter() - t0) * 1e3)
@@ -51,7 +55,7 @@ wall = time.perf_counter() - t_start
 # correctness on a sample (the stream lines carried no check): the same PCM of a few streams through a fresh
 # ONE-slot pool (= the single-stream predict_stream path the parity tests pin to the reference goldens) must give the same text
 verified = {}
-texts = {s: (out[s] or {}).get("text", "") for s in range(S)}
+texts = {s: last_result.get(s, {}).get("text", "") for s in range(S)}
 for s in sorted({0, S // 2, S - 1}):
     solo = StreamPool(eng, synth.vocabulary(), n_slots=1, max_frames=((total // 160) // 4 + 64))
     r = None
