@@ -105,11 +105,42 @@ __global__ void __launch_bounds__(256) ctc_topk_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// log(exp(a) + exp(b)) in a SPECIFIED sequence of correctly rounded float32 operations (no FMA contraction, no libm): the
+// same sequence as oracle/beam.py's exp32_det / log1p32_det, so kernel and restatement agree bit for bit — a pruned search over
+// hundreds of frames turns any 1-ulp score difference into a different beam.
+__device__ __forceinline__ float exp_det(float d) {                    // d <= 0
+    if (d < -87.0f) return 0.f;
+    const float n = rintf(__fmul_rn(d, 1.4426950408889634f));
+    float r = __fsub_rn(d, __fmul_rn(n, 0.693145751953125f));
+    r = __fsub_rn(r, __fmul_rn(n, 1.42860682030941723212e-6f));
+    float p = 1.0f / 720.0f;
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f / 120.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f / 24.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f / 6.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 0.5f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f);
+    p = __fadd_rn(__fmul_rn(p, r), 1.0f);
+    return __fmul_rn(p, __int_as_float(((int)n + 127) << 23));          // * 2^n (n in [-126, 0])
+}
+__device__ __forceinline__ float log1p_det(float u) {                  // 0 <= u <= 1: 2 atanh(u / (2 + u))
+    const float s = __fdiv_rn(u, __fadd_rn(2.0f, u));
+    const float z = __fmul_rn(s, s);
+    float p = 2.0f / 17.0f;
+    p = __fadd_rn(__fmul_rn(p, z), 2.0f / 15.0f);
+    p = __fadd_rn(__fmul_rn(p, z), 2.0f / 13.0f);
+    p = __fadd_rn(__fmul_rn(p, z), 2.0f / 11.0f);
+    p = __fadd_rn(__fmul_rn(p, z), 2.0f / 9.0f);
+    p = __fadd_rn(__fmul_rn(p, z), 2.0f / 7.0f);
+    p = __fadd_rn(__fmul_rn(p, z), 2.0f / 5.0f);
+    p = __fadd_rn(__fmul_rn(p, z), 2.0f / 3.0f);
+    p = __fadd_rn(__fmul_rn(p, z), 2.0f);
+    return __fmul_rn(s, p);
+}
 __device__ __forceinline__ float logaddexp_f(float a, float b) {
     if (a == -INFINITY) return b;
     if (b == -INFINITY) return a;
     const float hi = fmaxf(a, b), lo = fminf(a, b);
-    return hi + log1pf(expf(lo - hi));
+    return __fadd_rn(hi, log1p_det(exp_det(__fsub_rn(lo, hi))));
 }
 // order-preserving float -> uint key (larger float -> larger key); -inf maps lowest
 __device__ __forceinline__ uint32_t fkey(float f) {

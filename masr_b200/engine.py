@@ -510,7 +510,18 @@ class ConformerEngine:
         self._k("prefix_beam", "masr_ctc_prefix_beam", _p(ws["cand_id"]), _p(ws["cand_lp"]), _p(ws["cand_n"]), T, _p(ws["tlens"]),
                 B, int(beam_size), 0, _p(ws["beam_pool"]), _p(ws["trie_par"]), _p(ws["trie_tok"]), ws["trie_cap"],
                 _p(ws["beam_tok"]), ws["beam_tok"].shape[1], _p(ws["beam_n"]), _p(ws["beam_score"]))
+        self._last_beam = (ws, T, B)
         return ws["beam_tok"], ws["beam_n"], ws["beam_score"]
+
+    def last_beam_candidates(self):
+        """The pruned per-frame candidate lists [(token id, float32 log-probability)] the last ``ctc_beam`` call searched
+        over, per utterance and frame — what the top-k kernel handed to the prefix beam kernel (for parity tests: the CPU
+        restatement run on the same candidates must return the same prefix and score bit for bit)."""
+        ws, T, B = self._last_beam
+        n = ws["cand_n"][:B * T].cpu().numpy().reshape(B, T)
+        ids = ws["cand_id"][:B * T].cpu().numpy().reshape(B, T, -1)
+        lp = ws["cand_lp"][:B * T].cpu().numpy().reshape(B, T, -1)
+        return [[[(int(ids[b, t, k]), np.float32(lp[b, t, k])) for k in range(int(n[b, t]))] for t in range(T)] for b in range(B)]
 
     def transcribe_beam(self, waves: Sequence[np.ndarray], beam_size: int = 300, cutoff_prob: float = 0.99,
                         cutoff_top_n: int = 40, use_db_normalization: bool = True, target_db: float = -20.0):

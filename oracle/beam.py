@@ -30,15 +30,53 @@ import numpy as np
 NEG_INF = -float("inf")
 
 
+# ---- log-sum-exp in a SPECIFIED sequence of IEEE float32 operations --------------------------------------------------------
+# A pruned beam search over hundreds of frames amplifies a 1-ulp difference in any score into a different beam (near-tied
+# hypotheses swap ranks at the pruning boundary), so "the GPU kernel equals this restatement" is only testable if both evaluate
+# log(exp(a) + exp(b)) with the SAME rounding at every step.  libm's / CUDA's expf, log1pf differ in the last bit, so the
+# function is defined here operation by operation (one correctly rounded float32 +, -, *, / or round-to-nearest-even per
+# line; no fused multiply-add) and csrc/beam.cu evaluates exactly this sequence with __fmul_rn / __fadd_rn / __fdiv_rn.
+# Accuracy: a few ulp — irrelevant for the search; determinism is the point.
+_F = np.float32
+_LOG2E, _LN2_HI, _LN2_LO = _F(1.4426950408889634), _F(0.693145751953125), _F(1.42860682030941723212e-6)
+_EXP_C = [_F(1.0 / 720.0), _F(1.0 / 120.0), _F(1.0 / 24.0), _F(1.0 / 6.0), _F(0.5), _F(1.0), _F(1.0)]
+_ATANH_C = [_F(2.0 / 17.0), _F(2.0 / 15.0), _F(2.0 / 13.0), _F(2.0 / 11.0), _F(2.0 / 9.0), _F(2.0 / 7.0), _F(2.0 / 5.0), _F(2.0 / 3.0), _F(2.0)]
+
+
+def exp32_det(d: np.float32) -> np.float32:
+    """exp(d) for d <= 0: n = rint(d log2 e); r = d - n ln2 (two-step); degree-6 Horner; scale by 2^n."""
+    d = _F(d)
+    if d < _F(-87.0):
+        return _F(0.0)
+    n = np.rint(_F(d * _LOG2E))
+    r = _F(d - _F(n * _LN2_HI))
+    r = _F(r - _F(n * _LN2_LO))
+    p = _EXP_C[0]
+    for c in _EXP_C[1:]:
+        p = _F(_F(p * r) + c)
+    return _F(p * np.ldexp(_F(1.0), int(n)))
+
+
+def log1p32_det(u: np.float32) -> np.float32:
+    """log(1 + u) for 0 <= u <= 1 as 2 atanh(u / (2 + u)): s = u / (2 + u); z = s s; s * P(z), P of degree 8 in z."""
+    u = _F(u)
+    s = _F(u / _F(_F(2.0) + u))
+    z = _F(s * s)
+    p = _ATANH_C[0]
+    for c in _ATANH_C[1:]:
+        p = _F(_F(p * z) + c)
+    return _F(s * p)
+
+
 def logaddexp32(a: np.float32, b: np.float32) -> np.float32:
-    """float32 log-sum-exp exactly as the CUDA kernel evaluates it: max + log1p(exp(min - max))."""
-    a, b = np.float32(a), np.float32(b)
+    """float32 log-sum-exp exactly as the CUDA kernel evaluates it: max + log1p_det(exp_det(min - max))."""
+    a, b = _F(a), _F(b)
     if a == NEG_INF:
         return b
     if b == NEG_INF:
         return a
     hi, lo = (a, b) if a >= b else (b, a)
-    return np.float32(hi + np.float32(math.log1p(float(np.float32(math.exp(float(np.float32(lo - hi))))))))
+    return _F(hi + log1p32_det(exp32_det(_F(lo - hi))))
 
 
 def prune_frame(p: np.ndarray, cutoff_prob: float, cutoff_top_n: int) -> List[Tuple[int, np.float32]]:
@@ -54,15 +92,20 @@ def prune_frame(p: np.ndarray, cutoff_prob: float, cutoff_top_n: int) -> List[Tu
 
 
 def prefix_beam_search(probs: np.ndarray, beam_size: int = 300, cutoff_prob: float = 0.99, cutoff_top_n: int = 40,
-                       blank: int = 0, nbest: int = 1):
-    """probs [T, V] float32 posteriors -> list of (score float, token id list), best first."""
+                       blank: int = 0, nbest: int = 1, cands_per_frame=None):
+    """probs [T, V] float32 posteriors -> list of (score float, token id list), best first.
+    ``cands_per_frame`` (optional): per frame the already pruned candidate list [(token id, float32 log-probability)] — e.g.
+    the output of the CUDA top-k kernel — so that the SEARCH can be compared bit for bit (``probs`` is then only used for T)."""
     # a prefix is identified by a node id in a trie: node -> (parent node, last token); root = 0
     parent, last = [-1], [-1]
     child: Dict[Tuple[int, int], int] = {}
     beam = [(0, np.float32(0.0), np.float32(NEG_INF))]                       # (node, p_b, p_nb), best first
     for t in range(probs.shape[0]):
-        cands = [(c, np.float32(math.log(float(pc)))) for c, pc in prune_frame(probs[t], cutoff_prob, cutoff_top_n)
-                 if pc > 0]
+        if cands_per_frame is not None:
+            cands = [(int(c), np.float32(lp)) for c, lp in cands_per_frame[t]]
+        else:
+            cands = [(c, np.float32(math.log(float(pc)))) for c, pc in prune_frame(probs[t], cutoff_prob, cutoff_top_n)
+                     if pc > 0]
         new_b: Dict[int, np.float32] = {}
         new_nb: Dict[int, np.float32] = {}
         order: List[int] = []                                                # creation / first-touch order for tie-breaks

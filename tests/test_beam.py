@@ -91,12 +91,20 @@ def test_gpu_beam_equals_restatement(seed, T, beam, topn, cut):
     _lib.call("masr_ctc_prefix_beam", cid.data_ptr(), clp.data_ptr(), cn.data_ptr(), T, ld.data_ptr(), B, beam, 0, pool.data_ptr(),
               tp.data_ptr(), tt.data_ptr(), trie_n.value, otok.data_ptr(), T, on.data_ptr(), osc.data_ptr(), st)
     torch.cuda.synchronize()
+    clp_h = clp.cpu().numpy()
     for b in range(B):
         p = ph[b * T: b * T + lens[b]]
-        (score, toks), = obeam.prefix_beam_search(p, beam_size=beam, cutoff_prob=cut, cutoff_top_n=topn)
+        # the SEARCH, bit for bit: the restatement on the kernel's own candidate lists (both evaluate log-sum-exp in the same
+        # specified sequence of float32 operations) -> identical prefix and identical float32 score
+        cands = [[(int(cid_h[b * T + t, k]), clp_h[b * T + t, k]) for k in range(cn_h[b * T + t])] for t in range(lens[b])]
+        (score, toks), = obeam.prefix_beam_search(p, beam_size=beam, cutoff_prob=cut, cutoff_top_n=topn, cands_per_frame=cands)
         got = otok[b, :on[b].item()].cpu().tolist()
         assert got == toks, (b, got, toks)
-        assert abs(osc[b].item() - score) < 2e-3 * max(1.0, abs(score))
+        assert np.float32(osc[b].item()) == np.float32(score), (b, osc[b].item(), score)
+        # the candidate log-probabilities themselves: within float32 rounding of log(softmax)
+        for t in (0, lens[b] - 1):
+            for c, lp in cands[t]:
+                assert abs(float(lp) - np.log(float(p[t, c]))) < 2e-6 * max(1.0, abs(float(lp)))
 
 
 @pytest.mark.gpu

@@ -43,6 +43,8 @@ def check(eng, waves, ref_probs):
     difference in the inputs legitimately changes a pruned beam search, so decoder and encoder are compared separately."""
     toks, scores = shard.sharded_transcribe(waves, lambda ws: eng.transcribe_beam(ws, **BEAM), max_tokens=800)
     assert len(toks) == len(waves)
+    order = shard.partition([len(w) for w in waves], 1)[0]          # one rank: the shard is the whole list, longest first
+    cands = dict(zip(order, eng.last_beam_candidates()))
     for i, w in enumerate(waves):
         feat = ob.featurize(w.copy())
         want_probs = ref_probs(torch.from_numpy(feat)[None])
@@ -50,13 +52,14 @@ def check(eng, waves, ref_probs):
         assert probs.shape == want_probs.shape
         assert np.array_equal(probs.argmax(1), want_probs.argmax(1)), i
         assert np.abs(probs - want_probs).max() < 5e-5, i
-        (score, want), = obeam.prefix_beam_search(probs, **BEAM)
-        if toks[i] != want:
-            # a float32 beam search over hundreds of frames can resolve a near-tie between two hypotheses differently on the
-            # GPU (expf/log1pf within 1-2 ulp of the CPU's): accept only if both are equally likely under the exact CTC
-            # likelihood, and the reported scores agree
-            assert abs(ctc_loglik(probs, toks[i]) - ctc_loglik(probs, want)) < 2e-3, i
-        assert abs(scores[i] - score) < 5e-3 * max(1.0, abs(score)), i
+        # the search, bit for bit: restatement on the candidate lists the GPU searched over (same log-sum-exp operation
+        # sequence on both sides, oracle/beam.py) -> identical prefix, identical float32 score, at any utterance length
+        (score, want), = obeam.prefix_beam_search(probs, cands_per_frame=cands[i][:probs.shape[0]], **BEAM)
+        assert toks[i] == want, i
+        assert np.float32(scores[i]) == np.float32(score), i
+        # and the pruning: candidate ids per frame equal the restatement's prune of the engine's posteriors
+        for t in (0, probs.shape[0] // 2, probs.shape[0] - 1):
+            assert [c for c, _ in cands[i][t]] == [c for c, _ in obeam.prune_frame(probs[t], BEAM["cutoff_prob"], BEAM["cutoff_top_n"])], (i, t)
 
 
 def test_config4_efficient_conformer_nonstreaming_beam():
