@@ -77,12 +77,31 @@ __global__ void __launch_bounds__(LSTM_UNITS * 32) lstm_step_kernel(
 // and the steps are separated by a grid-wide barrier (one atomic counter; the grid has at most one CTA per SM, all
 // co-resident).  Same arithmetic per output as lstm_step_kernel except the order of the K sum (two interleaved partial sums).
 constexpr int LS_UNITS = 8;       // hidden units per CTA (one warp each)
-constexpr int LS_KC = 128;        // rows of h staged per window
+constexpr int LS_KC = 64;         // rows of h per shared-memory window (8 KB)
+constexpr int LS_NST = 4;         // windows in flight (cp.async ring)
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// packed fp32 FMA (Blackwell fma.rn.f32x2): two independent round-to-nearest FMAs per issue slot
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void ffma2(uint64_t& d, uint64_t a, uint64_t b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float sum2(uint64_t v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a + b;
+}
+__device__ __forceinline__ void cp_async16_cg(void* dst, const void* src) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 
 __global__ void __launch_bounds__(LS_UNITS * 32, 1) lstm_seq_kernel(
@@ -92,7 +111,7 @@ __global__ void __launch_bounds__(LS_UNITS * 32, 1) lstm_seq_kernel(
     unsigned* counter) {
     extern __shared__ __align__(16) float ls_smem[];
     float* Ws = ls_smem;                              // [LS_UNITS][4][H]
-    float* hs = ls_smem + (size_t)LS_UNITS * 4 * H;   // [2][LS_KC][32]
+    float* hs = ls_smem + (size_t)LS_UNITS * 4 * H;   // [LS_NST][LS_KC][32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int u0 = blockIdx.x * LS_UNITS, u = u0 + warp;
     const int nb = (B + LSTM_BP - 1) / LSTM_BP;
@@ -107,13 +126,29 @@ __global__ void __launch_bounds__(LS_UNITS * 32, 1) lstm_seq_kernel(
     __syncthreads();
     const float* wrow = Ws + (size_t)warp * 4 * H;
     const unsigned G = gridDim.x;
-    constexpr int PER = LS_KC * LSTM_BP / (LS_UNITS * 32 * 4);          // float4 per thread per window (= 4)
+    constexpr int WIN_F4 = LS_KC * LSTM_BP / 4;                          // 16-byte pieces per window (512)
+    const int nwin = H / LS_KC;
     for (int s = 0; s < T; ++s) {
         const float* hin = s == 0 ? h0_T : hbuf + (int64_t)((s - 1) & 1) * nb * chunk_elems;
         float* hout = hbuf + (int64_t)(s & 1) * nb * chunk_elems;
         for (int bc = 0; bc < nb; ++bc) {
             const float* hT = hin + (int64_t)bc * chunk_elems;
-            float ai0 = 0.f, af0 = 0.f, ag0 = 0.f, ao0 = 0.f, ai1 = 0.f, af1 = 0.f, ag1 = 0.f, ao1 = 0.f;
+            // window `w` of h_{t-1} -> ring slot w % LS_NST, straight from L2 into shared memory (cp.async.cg: no L1, so the
+            // other CTAs' writes of the previous step are seen)
+            auto issue = [&](int w) {
+                if (w < nwin) {
+                    const float* src = hT + (size_t)w * LS_KC * LSTM_BP;
+                    float* dst = hs + (size_t)(w % LS_NST) * LS_KC * LSTM_BP;
+#pragma unroll
+                    for (int j = 0; j < WIN_F4 / (LS_UNITS * 32); ++j) {
+                        const int e = (j * LS_UNITS * 32 + tid) * 4;
+                        cp_async16_cg(dst + e, src + e);
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");      // (possibly empty: keeps the group count uniform)
+            };
+#pragma unroll
+            for (int w = 0; w < LS_NST - 1; ++w) issue(w);
             // this lane's utterance: input gates, cell state and previous output are fetched now, consumed after the K loop
             const int b = bc * LSTM_BP + lane;
             const int len = b < B ? lens[b] : 0;
@@ -126,40 +161,33 @@ __global__ void __launch_bounds__(LS_UNITS * 32, 1) lstm_seq_kernel(
                 c_prev = c_state[(int64_t)b * H + u];
             }
             const float h_prev = __ldcg(hT + (int64_t)u * LSTM_BP + lane);
-            float4 pre[PER];
-#pragma unroll
-            for (int j = 0; j < PER; ++j) pre[j] = __ldcg(reinterpret_cast<const float4*>(hT) + j * LS_UNITS * 32 + tid);
-            const int nwin = H / LS_KC;
+            uint64_t ai = 0, af = 0, ag = 0, ao = 0;                       // (even-k, odd-k) partial sums of the four gates
             for (int win = 0; win < nwin; ++win) {
-                float* hb = hs + (size_t)(win & 1) * LS_KC * LSTM_BP;
-#pragma unroll
-                for (int j = 0; j < PER; ++j) *reinterpret_cast<float4*>(hb + (size_t)(j * LS_UNITS * 32 + tid) * 4) = pre[j];
-                __syncthreads();                           // window visible; the other buffer is free (read two windows ago)
-                if (win + 1 < nwin) {
-#pragma unroll
-                    for (int j = 0; j < PER; ++j)
-                        pre[j] = __ldcg(reinterpret_cast<const float4*>(hT + (size_t)(win + 1) * LS_KC * LSTM_BP) + j * LS_UNITS * 32 + tid);
-                }
+                asm volatile("cp.async.wait_group %0;" ::"n"(LS_NST - 2) : "memory");   // window `win` has landed (this thread's copies)
+                __syncthreads();                             // ... everybody's; and slot (win-1) % NST is no longer being read
+                issue(win + LS_NST - 1);
+                const float* hb = hs + (size_t)(win % LS_NST) * LS_KC * LSTM_BP;
                 const float* wk = wrow + win * LS_KC;
 #pragma unroll 4
                 for (int k = 0; k < LS_KC; k += 4) {
                     const float4 wi = *reinterpret_cast<const float4*>(wk + k), wf = *reinterpret_cast<const float4*>(wk + H + k);
                     const float4 wg = *reinterpret_cast<const float4*>(wk + 2 * H + k), wo = *reinterpret_cast<const float4*>(wk + 3 * H + k);
-                    const float h0 = hb[(k + 0) * LSTM_BP + lane], h1 = hb[(k + 1) * LSTM_BP + lane];
-                    const float h2 = hb[(k + 2) * LSTM_BP + lane], h3 = hb[(k + 3) * LSTM_BP + lane];
-                    ai0 = fmaf(wi.x, h0, ai0); ai1 = fmaf(wi.y, h1, ai1); ai0 = fmaf(wi.z, h2, ai0); ai1 = fmaf(wi.w, h3, ai1);
-                    af0 = fmaf(wf.x, h0, af0); af1 = fmaf(wf.y, h1, af1); af0 = fmaf(wf.z, h2, af0); af1 = fmaf(wf.w, h3, af1);
-                    ag0 = fmaf(wg.x, h0, ag0); ag1 = fmaf(wg.y, h1, ag1); ag0 = fmaf(wg.z, h2, ag0); ag1 = fmaf(wg.w, h3, ag1);
-                    ao0 = fmaf(wo.x, h0, ao0); ao1 = fmaf(wo.y, h1, ao1); ao0 = fmaf(wo.z, h2, ao0); ao1 = fmaf(wo.w, h3, ao1);
+                    const uint64_t h01 = pack2(hb[(k + 0) * LSTM_BP + lane], hb[(k + 1) * LSTM_BP + lane]);
+                    const uint64_t h23 = pack2(hb[(k + 2) * LSTM_BP + lane], hb[(k + 3) * LSTM_BP + lane]);
+                    ffma2(ai, pack2(wi.x, wi.y), h01); ffma2(ai, pack2(wi.z, wi.w), h23);
+                    ffma2(af, pack2(wf.x, wf.y), h01); ffma2(af, pack2(wf.z, wf.w), h23);
+                    ffma2(ag, pack2(wg.x, wg.y), h01); ffma2(ag, pack2(wg.z, wg.w), h23);
+                    ffma2(ao, pack2(wo.x, wo.y), h01); ffma2(ao, pack2(wo.z, wo.w), h23);
                 }
             }
-            __syncthreads();                               // all warps are done with both windows before the next chunk refills them
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                               // all warps are done with the ring before the next chunk / step refills it
             float* hTo = hout + (int64_t)bc * chunk_elems + (int64_t)u * LSTM_BP + lane;
             if (!active) {
                 *hTo = h_prev;                              // finished (or padding lane): state frozen
             } else {
-                const float gi = sigmoid_f(gxi + (ai0 + ai1)), gf = sigmoid_f(gxf + (af0 + af1));
-                const float gg = tanhf(gxg + (ag0 + ag1)), go = sigmoid_f(gxo + (ao0 + ao1));
+                const float gi = sigmoid_f(gxi + sum2(ai)), gf = sigmoid_f(gxf + sum2(af));
+                const float gg = tanhf(gxg + sum2(ag)), go = sigmoid_f(gxo + sum2(ao));
                 const float c = gf * c_prev + gi * gg;
                 const float h = go * tanhf(c);
                 c_state[(int64_t)b * H + u] = c;
@@ -209,7 +237,7 @@ extern "C" int masr_lstm_seq_f32(const float* gates_x, int64_t ldg, int64_t bstr
                                  void* stream) {
     if (B == 0) return MASR_OK;
     MASR_REQUIRE(gates_x && Whh && h0_T && hN_T && c_state && lens && workspace && (out || (outh && outl)), "masr_lstm_seq_f32: null pointer");
-    MASR_REQUIRE(H % LS_KC == 0 && H % LS_UNITS == 0 && H <= 1024, "masr_lstm_seq_f32: H=%d unsupported (multiple of %d, <= 1024)", H, LS_KC);
+    MASR_REQUIRE(H % 128 == 0 && H <= 1024, "masr_lstm_seq_f32: H=%d unsupported (multiple of 128, <= 1024)", H);
     int64_t need = 0;
     masr_lstm_seq_workspace_bytes(B, H, &need);
     MASR_REQUIRE(workspace_bytes >= need, "masr_lstm_seq_f32: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
@@ -218,7 +246,7 @@ extern "C" int masr_lstm_seq_f32(const float* gates_x, int64_t ldg, int64_t bstr
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = H / LS_UNITS;
     MASR_REQUIRE(grid <= sms, "masr_lstm_seq_f32: %d CTAs cannot be co-resident on %d SMs", grid, sms);
-    const size_t smem = ((size_t)LS_UNITS * 4 * H + 2 * LS_KC * LSTM_BP) * sizeof(float);
+    const size_t smem = ((size_t)LS_UNITS * 4 * H + (size_t)LS_NST * LS_KC * LSTM_BP) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error("lstm_seq smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     const int nb = (B + LSTM_BP - 1) / LSTM_BP;
