@@ -202,6 +202,7 @@ def main():
         # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")       # whatever NCCL logs must not land on stdout
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     _b.build()
@@ -497,6 +498,13 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if graph_gather:
+            # CUDA graphs that captured NCCL kernels still reference the communicator; destroy_process_group() then waits
+            # forever (seen at N=2, r02).  Everything is measured and printed: leave without tearing NCCL down.
+            os._exit(0)
         dist.destroy_process_group()
 
 
