@@ -161,9 +161,14 @@ struct BeamShared {
     float clp[BK_MAX];
     int scan[BEAM_THREADS];
     int misc[8];
+    int wsum[2][BEAM_THREADS / 32];              // per-warp (gt | eq << 16) counts of the ordered compaction, double-buffered
+    float r_score[BEAM_CAP];                     // survivors in rank order
+    int r_src[BEAM_CAP];
 };
 
-// pool layout: [0, BEAM_CAP) existing prefixes (rank order), then BEAM_CAP + i*K + k children of (rank i, candidate k)
+// pool layout: [0, BEAM_CAP) existing prefixes (rank order), then BEAM_CAP + i*K + k children of (rank i, candidate k);
+// K = this frame's candidate count (usually a handful, cutoff_prob 0.99), so the pool the selection scans is 512 + beam*K
+// entries, not 512 + beam*40
 __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
     const int* __restrict__ cand_id, const float* __restrict__ cand_logp, const int* __restrict__ cand_cnt, int64_t bstride,
     const int* __restrict__ lens, int beam, int blank, float* __restrict__ pool_all, int* __restrict__ trie_parent,
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
         const int K = cand_cnt[row];
         if (tid < K) { S.cid[tid] = cand_id[row * BK_MAX + tid]; S.clp[tid] = cand_logp[row * BK_MAX + tid]; }
         for (int i = tid; i < 2 * BEAM_CAP; i += BEAM_THREADS) S.hkey[i] = -1;
-        const int pool_n = BEAM_CAP + nbeam * BK_MAX;
+        const int pool_n = BEAM_CAP + nbeam * K;
         for (int i = tid; i < pool_n; i += BEAM_THREADS) pool[i] = -INFINITY;
         __syncthreads();
         // node id -> rank hash; stay transitions (blank / repeated token) of the existing prefixes
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
             float add;
             if (c == S.last[i]) add = S.pb[i] == -INFINITY ? -INFINITY : S.pb[i] + S.clp[k];
             else add = S.score[i] + S.clp[k];
-            pool[BEAM_CAP + i * BK_MAX + k] = add;
+            pool[BEAM_CAP + i * K + k] = add;
         }
         __syncthreads();
         // children that already exist as beam entries: fold their contribution into that entry (one pair per entry)
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
             if (pi >= 0) {
                 for (int k = 0; k < K; ++k)
                     if (S.cid[k] == S.last[tid]) {
-                        const int slot = BEAM_CAP + pi * BK_MAX + k;
+                        const int slot = BEAM_CAP + pi * K + k;
                         S.nnb[tid] = logaddexp_f(S.nnb[tid], pool[slot]);
                         pool[slot] = -INFINITY;
                         break;
@@ -280,12 +285,14 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
             want = S.misc[1];
             __syncthreads();
         }
-        // threshold key = prefix; take everything above it, and the first `want` (pool order) equal to it
-        // ordered compaction: chunked exclusive scan over the pool
-        int base_gt = 0;
-        if (tid == 0) { S.misc[2] = 0; S.misc[3] = 0; }
-        __syncthreads();
-        for (int start = 0; start < pool_n; start += BEAM_THREADS) {
+        // threshold key = prefix; take everything above it, and the first `want` (pool order) equal to it.
+        // Ordered compaction: per chunk of 512 pool entries one ballot per warp + the 16 warp counts through shared memory
+        // (double-buffered: one block barrier per chunk; the first version ran a 9-step shared-memory scan per chunk).
+        const int lane_ = tid & 31, warp_ = tid >> 5;
+        const unsigned lt_mask = (1u << lane_) - 1u;
+        int run_gt = 0, run_eq = 0;                                             // identical in every thread
+        int chunk = 0;
+        for (int start = 0; start < pool_n; start += BEAM_THREADS, ++chunk) {
             const int i = start + tid;
             int is_gt = 0, is_eq = 0;
             if (i < pool_n && pool[i] != -INFINITY) {
@@ -293,59 +300,57 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
                 is_gt = kx > prefix;
                 is_eq = kx == prefix;
             }
-            // block scan of (gt, eq) packed
-            S.scan[tid] = (is_gt << 16) | is_eq;
+            const unsigned bg = __ballot_sync(0xffffffffu, is_gt), be = __ballot_sync(0xffffffffu, is_eq);
+            if (lane_ == 0) S.wsum[chunk & 1][warp_] = __popc(bg) | (__popc(be) << 16);
             __syncthreads();
-            for (int off = 1; off < BEAM_THREADS; off <<= 1) {
-                int v = tid >= off ? S.scan[tid - off] : 0;
-                __syncthreads();
-                S.scan[tid] += v;
-                __syncthreads();
+            int off_g = 0, off_e = 0, tot_g = 0, tot_e = 0;
+#pragma unroll
+            for (int w = 0; w < BEAM_THREADS / 32; ++w) {
+                const int v = S.wsum[chunk & 1][w];
+                if (w < warp_) { off_g += v & 0xFFFF; off_e += v >> 16; }
+                tot_g += v & 0xFFFF; tot_e += v >> 16;
             }
-            const int incl = S.scan[tid];
-            const int gt_before = S.misc[2] + (incl >> 16) - is_gt;
-            const int eq_before = S.misc[3] + (incl & 0xFFFF) - is_eq;
+            const int gt_before = run_gt + off_g + __popc(bg & lt_mask);
+            const int eq_before = run_eq + off_e + __popc(be & lt_mask);
             if (is_gt) S.s_src[gt_before] = i;                                  // provisional: gt entries first
             if (is_eq && eq_before < want) S.s_src[BEAM_CAP - 1 - eq_before] = i; // eq entries parked at the tail
-            __syncthreads();
-            if (tid == BEAM_THREADS - 1) { S.misc[2] += incl >> 16; S.misc[3] += incl & 0xFFFF; }
-            __syncthreads();
+            run_gt += tot_g; run_eq += tot_e;
         }
-        const int n_gt = S.misc[2];
-        const int n_eq = min(S.misc[3], want);
+        __syncthreads();
+        const int n_gt = run_gt;
+        const int n_eq = min(run_eq, want);
         const int n_sel = n_gt + n_eq;
+        if (tid < n_eq) S.s_score[tid] = __int_as_float(S.s_src[BEAM_CAP - 1 - tid]);   // (staged: the tail may overlap [n_gt, n_sel))
         __syncthreads();
-        if (tid < n_eq) S.s_src[n_gt + tid] = S.s_src[BEAM_CAP - 1 - tid];
+        if (tid < n_eq) S.s_src[n_gt + tid] = __float_as_int(S.s_score[tid]);
         __syncthreads();
-        // ---- rank the survivors: bitonic sort by (score desc, pool index asc) ----
+        // ---- rank the survivors by (score desc, pool index asc): every thread counts the entries that precede its own
+        //      (<= beam broadcast reads from shared memory, no barriers; the first version ran a 45-barrier bitonic sort) ----
         {
             float ks = -INFINITY;
             int ki = 0x7fffffff;
             if (tid < n_sel) { ki = S.s_src[tid]; ks = pool[ki]; }
             S.s_score[tid] = ks; S.scan[tid] = ki;
             __syncthreads();
-            for (int size = 2; size <= BEAM_CAP; size <<= 1)
-                for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                    const int j = tid ^ stride;
-                    if (j > tid) {
-                        const float a = S.s_score[tid], c = S.s_score[j];
-                        const int ai = S.scan[tid], ci = S.scan[j];
-                        const bool a_first = (a > c) || (a == c && ai < ci);      // desired order: a before c
-                        const bool up = (tid & size) == 0;
-                        if (up ? !a_first : a_first) { S.s_score[tid] = c; S.s_score[j] = a; S.scan[tid] = ci; S.scan[j] = ai; }
-                    }
-                    __syncthreads();
+            if (tid < n_sel) {
+                int rank = 0;
+                for (int j = 0; j < n_sel; ++j) {
+                    const float c = S.s_score[j];
+                    rank += (c > ks) || (c == ks && S.scan[j] < ki);
                 }
+                S.r_score[rank] = ks; S.r_src[rank] = ki;
+            }
+            __syncthreads();
         }
         // ---- materialise the new beam ----
         if (tid < n_sel) {
-            const int src = S.scan[tid];
+            const int src = S.r_src[tid];
             if (src < BEAM_CAP) {                     // an existing prefix survives
                 S.s_node[tid] = S.node[src]; S.s_par[tid] = S.par[src]; S.s_last[tid] = S.last[src];
                 S.s_pb[tid] = S.nb[src]; S.s_pnb[tid] = S.nnb[src];
                 S.s_src[tid] = -1;
             } else {                                  // a new child: gets a trie node below
-                const int i = (src - BEAM_CAP) / BK_MAX, k = (src - BEAM_CAP) - i * BK_MAX;
+                const int i = (src - BEAM_CAP) / K, k = (src - BEAM_CAP) - i * K;
                 S.s_node[tid] = -1; S.s_par[tid] = S.node[i]; S.s_last[tid] = S.cid[k];
                 S.s_pb[tid] = -INFINITY; S.s_pnb[tid] = pool[src];
                 S.s_src[tid] = 1;
@@ -367,13 +372,16 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
             S.s_node[tid] = found;
             need_new = found < 0;
         }
-        S.scan[tid] = need_new;
-        __syncthreads();
-        for (int off = 1; off < BEAM_THREADS; off <<= 1) {
-            int v = tid >= off ? S.scan[tid - off] : 0;
+        int new_total;
+        {
+            const unsigned bn = __ballot_sync(0xffffffffu, need_new);
+            if (lane_ == 0) S.wsum[0][warp_] = __popc(bn);
             __syncthreads();
-            S.scan[tid] += v;
-            __syncthreads();
+            int off = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < BEAM_THREADS / 32; ++w) { const int v = S.wsum[0][w]; if (w < warp_) off += v; tot += v; }
+            S.scan[tid] = off + __popc(bn & lt_mask) + need_new;              // inclusive count, as before
+            new_total = tot;
         }
         if (need_new) {
             const int id = nnodes + S.scan[tid] - 1;          // rank order (deterministic)
@@ -385,12 +393,11 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
                 while (atomicCAS(&thash[h], -1, id) != -1) h = h + 1 == hcap ? 0 : h + 1;
             }
         }
-        if (tid == BEAM_THREADS - 1) S.misc[4] = nnodes + S.scan[tid];
         __syncthreads();
-        nnodes = S.misc[4];
+        nnodes += new_total;
         if (tid < n_sel) {
             S.node[tid] = S.s_node[tid]; S.par[tid] = S.s_par[tid]; S.last[tid] = S.s_last[tid];
-            S.pb[tid] = S.s_pb[tid]; S.pnb[tid] = S.s_pnb[tid]; S.score[tid] = S.s_score[tid];
+            S.pb[tid] = S.s_pb[tid]; S.pnb[tid] = S.s_pnb[tid]; S.score[tid] = S.r_score[tid];
         }
         nbeam = n_sel;
         __syncthreads();
