@@ -23,6 +23,7 @@ from ._lib import EPI_BIAS, EPI_BIAS_GLU, EPI_BIAS_SCALE, EPI_BIAS_SILU, EPI_RES
 from .weights import ConformerWeights, load_state_dict, pack_conformer
 
 FRAME_LEN, FRAME_SHIFT, NUM_MEL = 400, 160, 80
+_NVTX = os.environ.get("MASR_NVTX", "0") == "1"
 
 
 def num_frames(num_samples: int) -> int:
@@ -179,9 +180,15 @@ class ConformerEngine:
         self.launches += 1
 
     def _k(self, tag, name, *args, n=1):
-        """One ABI call = `n` kernel launches on the current stream, optionally event-timed under `tag`."""
+        """One ABI call = `n` kernel launches on the current stream, optionally event-timed under `tag`.
+        MASR_NVTX=1 wraps every call in an NVTX range named after its tag (ffn_w1, attention, ctc_head ...), so the stages of
+        a step can be told apart on an Nsight Systems / Compute timeline."""
         ev = self._prof_begin(tag)
+        if _NVTX:
+            torch.cuda.nvtx.range_push(tag)
         call(name, *args, self._stream())
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         self._prof_end(ev)
         self.launches += n
 

@@ -33,7 +33,9 @@ else:
     eng = ConformerEngine(synth.conformer_state_dict(0), streaming=True)
 S, PUSH = args.streams, 8000
 total = (args.warm + args.pushes) * PUSH
-pcm = [(np.clip(synth.noise_audio(500 + s, total), -1, 1) * 32767).astype("<i2") for s in range(S)]
+# every fourth stream carries speech-like audio (non-empty transcripts for the correctness check), the rest noise
+pcm = [(np.clip(synth.speechlike_audio(500 + s, total) if s % 4 == 0 else synth.noise_audio(500 + s, total), -1, 1) * 32767).astype("<i2")
+       for s in range(S)]
 pool = StreamPool(eng, synth.vocabulary(), n_slots=S, max_frames=((total // 160) // 4 + 64))
 lat = []
 last_result = {}
@@ -61,7 +63,7 @@ for s in sorted({0, S // 2, S - 1}):
     r = None
     for k in range(args.warm + args.pushes):
         r = solo.push({0: pcm[s][k * PUSH:(k + 1) * PUSH].tobytes()}, is_end=False)[0] or r
-    verified[s] = bool(r is not None and r["text"] == texts[s])
+    verified[s] = bool(r is not None and r["text"] == texts[s] and (s % 4 != 0 or len(r["text"]) > 0))
 assert all(verified.values()), verified
 audio = S * args.pushes * PUSH / 16000.0
 lat = np.asarray(lat)
