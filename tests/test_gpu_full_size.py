@@ -45,7 +45,9 @@ def oracle_pass(sd, cfg, waves, vocab):
 @pytest.mark.parametrize("streaming,wseed", [(True, 0), (False, 1)], ids=["config1_headline_causal", "config2_noncausal"])
 def test_32x10s_full_batch_ids_bit_exact(gpu_engines, streaming, wseed, tmp_path):
     eng = gpu_engines(wseed, streaming)
-    waves = bench_waves()
+    # config 1: exactly the batch bench.py times; config 2: every other utterance speech-like (the non-causal synthetic model
+    # answers pure noise with blanks only, which would make the token comparison vacuous)
+    waves = bench_waves() if streaming else [make_audio("speech" if i % 2 else "noise", 1000 + i, 160000) for i in range(32)]
     res = eng.transcribe(waves, return_frames=True)              # the CUDA-graph device step of bench.py's `value`
     ref = oracle_pass(synth.to_torch(synth_weights(wseed)), oc.ConformerConfig(causal=streaming), waves, synth.vocabulary())
     mism = 0
@@ -56,7 +58,7 @@ def test_32x10s_full_batch_ids_bit_exact(gpu_engines, streaming, wseed, tmp_path
         assert toks == res.tokens[i], i
         assert abs(score - res.scores[i]) < SCORE_TOL, i
     assert mism == 0                                             # 32 x 248 = 7936 frames, all bit-exact
-    assert sum(len(t) for t in res.tokens) >= 32                 # ... and the comparison is not vacuous (non-blank output)
+    assert sum(len(t) for t in res.tokens) >= 16                 # ... and the comparison is not vacuous (non-blank output)
     # the same batch through the user-facing pipelined API (bench.py's `e2e`)
     from masr_b200.predict import MASRPredictor
     mp, vp = str(tmp_path / "m.pt"), str(tmp_path / "vocabulary.txt")
