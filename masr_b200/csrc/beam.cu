@@ -271,13 +271,26 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
                 if ((kx & mask) == prefix && pool[i] != -INFINITY) atomicAdd(&S.hist[(kx >> (pass * 8)) & 255], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                int acc = 0, d = 255;
-                for (; d > 0; --d) {
-                    if (acc + (int)S.hist[d] >= want) break;
-                    acc += S.hist[d];
+            // the digit where the descending cumulative count reaches `want`: inclusive scan over the 256 bins by 8 warps
+            // (the first version walked the bins serially in thread 0 — a third of the kernel's time in the r02 capture)
+            {
+                int v = 0, incl = 0;
+                if (tid < 256) {
+                    v = (int)S.hist[255 - tid];                     // position tid <-> digit 255 - tid
+                    incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((tid & 31) >= o) incl += u;
+                    }
+                    if ((tid & 31) == 31) S.wsum[0][tid >> 5] = incl;
                 }
-                S.misc[0] = d; S.misc[1] = want - acc;
+                __syncthreads();
+                if (tid < 256) {
+                    for (int w = 0; w < (tid >> 5); ++w) incl += S.wsum[0][w];
+                    const int excl = incl - v;
+                    if (excl < want && (incl >= want || tid == 255)) { S.misc[0] = 255 - tid; S.misc[1] = want - excl; }
+                }
             }
             __syncthreads();
             prefix |= (uint32_t)S.misc[0] << (pass * 8);
@@ -324,22 +337,34 @@ __global__ void __launch_bounds__(BEAM_THREADS) prefix_beam_kernel(
         __syncthreads();
         if (tid < n_eq) S.s_src[n_gt + tid] = __float_as_int(S.s_score[tid]);
         __syncthreads();
-        // ---- rank the survivors by (score desc, pool index asc): every thread counts the entries that precede its own
-        //      (<= beam broadcast reads from shared memory, no barriers; the first version ran a 45-barrier bitonic sort) ----
+        // ---- rank the survivors by (score desc, pool index asc): bitonic sort of the 512 (score, index) pairs held one per
+        //      thread; compare-exchange distances below 32 go through warp shuffles, only the 10 distances >= 32 through shared
+        //      memory (the first version: 45 block barriers; rank-by-counting was tried in between and was slower) ----
         {
             float ks = -INFINITY;
             int ki = 0x7fffffff;
             if (tid < n_sel) { ki = S.s_src[tid]; ks = pool[ki]; }
-            S.s_score[tid] = ks; S.scan[tid] = ki;
-            __syncthreads();
-            if (tid < n_sel) {
-                int rank = 0;
-                for (int j = 0; j < n_sel; ++j) {
-                    const float c = S.s_score[j];
-                    rank += (c > ks) || (c == ks && S.scan[j] < ki);
+            for (int size = 2; size <= BEAM_CAP; size <<= 1) {
+                const bool up = (tid & size) == 0;
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    float c;
+                    int ci;
+                    if (stride >= 32) {
+                        __syncthreads();                         // (previous readers of the exchange buffers are done)
+                        S.s_score[tid] = ks; S.scan[tid] = ki;
+                        __syncthreads();
+                        c = S.s_score[tid ^ stride]; ci = S.scan[tid ^ stride];
+                    } else {
+                        c = __shfl_xor_sync(0xffffffffu, ks, stride);
+                        ci = __shfl_xor_sync(0xffffffffu, ki, stride);
+                    }
+                    const bool mine_first = (ks > c) || (ks == c && ki < ci);
+                    const bool want_first = ((tid & stride) == 0) == up;
+                    if (mine_first != want_first) { ks = c; ki = ci; }
                 }
-                S.r_score[rank] = ks; S.r_src[rank] = ki;
             }
+            __syncthreads();
+            if (tid < n_sel) { S.r_score[tid] = ks; S.r_src[tid] = ki; }
             __syncthreads();
         }
         // ---- materialise the new beam ----
