@@ -536,6 +536,84 @@ class ConformerEngine:
         feats, frames, status = self.fbank(waves, use_db_normalization, target_db)
         return self.beam_features(feats, frames, beam_size, cutoff_prob, cutoff_top_n)
 
+    def transcribe_beam_pipelined(self, batches, beam_size: int = 300, cutoff_prob: float = 0.99, cutoff_top_n: int = 40,
+                                  use_db_normalization: bool = True, target_db: float = -20.0):
+        """Generator over ``batches`` (iterable of lists of float32 waveforms) yielding ``transcribe_beam(batch)`` per batch, in
+        order, one batch late.  The prefix beam search is one CTA per utterance — 32 of 148 SMs busy for milliseconds — so it
+        runs on a SECOND stream, concurrently with the fbank / encoder / top-k kernels of the next batch on the idle SMs
+        (two sets of candidate / trie / output buffers).  Same results as the blocking call."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_beam_stream", None) is None:
+            self._beam_stream = torch.cuda.Stream(device=dev)
+            self._beam_slots = [dict(), dict()]
+        side = self._beam_stream
+        prev = None
+        k = 0
+
+        def finish(item):
+            slot, B = item
+            if B == 0:
+                return [], []
+            slot["done"].synchronize()
+            n = slot["h_n"][:B].numpy()
+            tok = slot["h_tok"][:B].numpy()
+            sc = slot["h_sc"][:B].numpy()
+            self.d2h_bytes += tok.nbytes + n.nbytes + sc.nbytes
+            return [tok[b, :n[b]].tolist() for b in range(B)], [float(x) for x in sc]
+
+        for waves in batches:
+            slot = self._beam_slots[k & 1]
+            k += 1
+            B = len(waves)
+            if B == 0:
+                item = (slot, 0)
+            else:
+                if "done" in slot:
+                    main.wait_event(slot["done"])          # the slot's previous search (batch k-2) has consumed its buffers
+                feats, frames, status = self.fbank(waves, use_db_normalization, target_db)
+                enc, tl, T, ws = self.encode(feats, frames)
+                M = B * max(1, T)
+                if slot.get("M", 0) < M or slot.get("B", 0) < B or slot.get("T", 0) < T:
+                    pool_n, trie_n = _lib.C.c_int64(0), _lib.C.c_int64(0)
+                    call("masr_ctc_prefix_beam_workspace", B, max(1, T), _lib.C.byref(pool_n), _lib.C.byref(trie_n))
+                    i32, f32 = torch.int32, torch.float32
+                    slot.update(M=M, B=B, T=T, trie_cap=trie_n.value,
+                                cand_id=torch.empty(M, 40, device=dev, dtype=i32), cand_lp=torch.empty(M, 40, device=dev, dtype=f32),
+                                cand_n=torch.empty(M, device=dev, dtype=i32), pool=torch.empty(pool_n.value, device=dev, dtype=f32),
+                                trie_par=torch.empty(B * trie_n.value, device=dev, dtype=i32),
+                                trie_tok=torch.empty(B * trie_n.value, device=dev, dtype=i32),
+                                tok=torch.zeros(B, max(1, T), device=dev, dtype=i32), n=torch.zeros(B, device=dev, dtype=i32),
+                                sc=torch.zeros(B, device=dev, dtype=f32), tlens=torch.zeros(B, device=dev, dtype=i32),
+                                h_tok=torch.zeros(B, max(1, T), dtype=i32, pin_memory=True), h_n=torch.zeros(B, dtype=i32, pin_memory=True),
+                                h_sc=torch.zeros(B, dtype=f32, pin_memory=True), ready=torch.cuda.Event(), done=torch.cuda.Event())
+                if T == 0:
+                    slot["h_n"][:B].zero_()
+                    slot["h_sc"][:B].zero_()
+                    slot["done"].record(main)
+                    item = (slot, B)
+                else:
+                    logits = self.ctc_logits(enc, ws)
+                    self._k("ctc_topk", "masr_ctc_topk_f32", _p(logits), self.Vpad, B * T, self.V, int(cutoff_top_n), float(cutoff_prob),
+                            _p(slot["cand_id"]), _p(slot["cand_lp"]), _p(slot["cand_n"]))
+                    slot["tlens"][:B].copy_(ws["tlens"][:B])
+                    slot["ready"].record(main)
+                    side.wait_event(slot["ready"])
+                    with torch.cuda.stream(side):
+                        self._k("prefix_beam", "masr_ctc_prefix_beam", _p(slot["cand_id"]), _p(slot["cand_lp"]), _p(slot["cand_n"]), T,
+                                _p(slot["tlens"]), B, int(beam_size), 0, _p(slot["pool"]), _p(slot["trie_par"]), _p(slot["trie_tok"]),
+                                slot["trie_cap"], _p(slot["tok"]), slot["tok"].shape[1], _p(slot["n"]), _p(slot["sc"]))
+                        slot["h_tok"][:B, :slot["tok"].shape[1]].copy_(slot["tok"][:B], non_blocking=True)
+                        slot["h_n"][:B].copy_(slot["n"][:B], non_blocking=True)
+                        slot["h_sc"][:B].copy_(slot["sc"][:B], non_blocking=True)
+                        slot["done"].record(side)
+                    item = (slot, B)
+            if prev is not None:
+                yield finish(prev)
+            prev = item
+        if prev is not None:
+            yield finish(prev)
+
     def beam_features(self, feats, frames, beam_size: int = 300, cutoff_prob: float = 0.99, cutoff_top_n: int = 40):
         B = feats.shape[0]
         enc, tl, T, ws = self.encode(feats, frames)

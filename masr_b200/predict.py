@@ -179,11 +179,21 @@ class MASRPredictor:
         order; element i of batch k equals ``predict(batches[k][i])``.  Host staging and the H2D copy of batch k+1 overlap
         the GPU pass of batch k (``ConformerEngine.transcribe_pipelined``), so the results lag the input by one batch.
         Greedy decoding only.  ``device_hook``: see ``transcribe_pipelined`` (cross-rank gather of a sharded deployment)."""
-        if self._beam_conf is not None:
-            for b in batches:
-                yield self.predict_batch(b, sample_rate)
-            return
         vocab = self._text_featurizer.vocab_list
+        if self._beam_conf is not None:
+            # the prefix beam search of batch k runs on a second stream under the encoder of batch k+1
+            def loaded_b():
+                for audio_list in batches:
+                    waves = []
+                    for a in audio_list:
+                        s, sr = load_audio(a, sample_rate)
+                        self._check_rate(sr)
+                        waves.append(s)
+                    yield waves
+            for toks, scores in self.predictor.transcribe_beam_pipelined(loaded_b(), use_db_normalization=self._use_db,
+                                                                         target_db=self._target_db, **self._beam_conf):
+                yield [{'text': ids_to_text(t, vocab), 'score': s} for t, s in zip(toks, scores)]
+            return
 
         def loaded():
             for audio_list in batches:

@@ -88,3 +88,22 @@ def test_config5_conformer_variable_length_1_to_30s_beam(gpu_engines):
         with torch.no_grad():
             return oc.get_encoder_out(sd, cfg, feat)[0].numpy()
     check(eng, waves, ref)
+
+
+def test_pipelined_beam_equals_blocking_calls(gpu_engines):
+    """`transcribe_beam_pipelined`: the prefix beam search of batch k on a second stream under the encoder of batch k+1 (two
+    buffer sets, results one batch late) returns exactly what one blocking `transcribe_beam` per batch returns — ragged batches,
+    changing batch sizes, an empty batch and a batch of too-short audio included."""
+    eng = gpu_engines(0, True)
+    rng = np.random.default_rng(11)
+    batches = []
+    for k, B in enumerate((5, 3, 0, 7, 2, 6)):
+        batches.append([make_audio("speech" if (i + k) % 2 else "noise", 900 + 10 * k + i, int(rng.integers(8000, 16000 * 4))) for i in range(B)])
+    batches.append([make_audio("noise", 990, 300)])                      # shorter than one frame: no output frames at all
+    want = [eng.transcribe_beam(b, **BEAM) if b else ([], []) for b in batches]
+    got = list(eng.transcribe_beam_pipelined(iter(batches), **BEAM))
+    assert len(got) == len(want)
+    for (gt, gs), (wt, ws) in zip(got, want):
+        assert gt == wt
+        assert [np.float32(x) for x in gs] == [np.float32(x) for x in ws]
+    assert sum(len(t) for gt, _ in got for t in gt) > 10

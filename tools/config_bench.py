@@ -72,6 +72,23 @@ del e
 sdn = synth.efficient_conformer_state_dict(0)
 e = EfficientConformerEngine(sdn, streaming=False)
 run("config4 efficient_conformer.yml streaming=False 32x10s/GPU ctc_beam_search(300,40,0.99,no LM)", e, tens, lambda w: e.transcribe_beam(w, **BEAM))
+def piped(w, e_=None):
+    return list(e.transcribe_beam_pipelined([w] * 4, **BEAM))[-1]
+
+
+if not only or "config4p" in only:
+    # throughput form of config 4: a stream of batches, the beam search of batch k under the encoder of batch k+1
+    for _ in range(2):
+        piped(tens)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    n_b = 12
+    res = list(e.transcribe_beam_pipelined([tens] * n_b, **BEAM))
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n_b
+    same = res[-1][0] == e.transcribe_beam(tens, **BEAM)[0]
+    assert same
+    print(json.dumps({"config": "config4p efficient_conformer.yml streaming=False 32x10s/GPU ctc_beam_search, PIPELINED stream of batches (beam search of batch k on a second stream under the encoder of batch k+1)",
+                      "utterances": 32, "audio_s": 320.0, "ms_per_batch": dt * 1e3, "audio_seconds_per_second": 320.0 / dt,
+                      "equals_blocking_call": bool(same)}), flush=True)
 run("config4g efficient_conformer.yml streaming=False 32x10s/GPU ctc_greedy", e, tens, lambda w: e.transcribe(w),
     oracle=greedy_oracle(oe, synth.to_torch(sdn), oe.EfficientConfig(causal=False)), sample=(0, 31))
 del e
