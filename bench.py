@@ -198,6 +198,23 @@ def main():
         _b.build()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and os.environ.get("MASR_BENCH_AFFINITY", "1") != "0":
+        # one process per GPU: keep this rank's staging threads and its pinned buffers on the CPUs / NUMA node next to ITS GPU
+        # (8 ranks x (4 stager threads + 20 MB pinned memcpy per step) otherwise contend across sockets: e2e efficiency 0.91 at N=8 in r01)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            ncpu = os.cpu_count() or 1
+            masks = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = {64 * i + b for i, m in enumerate(masks) for b in range(64) if (m >> b) & 1}
+            cpus &= set(os.sched_getaffinity(0))
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = f"{len(cpus)} GPU-local CPUs"
+        except Exception as e:                      # best effort: no NVML / no permission -> default placement
+            numa = f"unavailable ({type(e).__name__})"
     if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -492,6 +509,7 @@ def main():
                 "cpu_baseline": cpu}
         if world > 1:
             line["gather_verified"] = gather_verified
+            line["config"]["cpu_affinity"] = numa
             line["config"]["collective"] = ("all_gather_into_tensor of the packed int32 outputs, captured in the step's CUDA graph"
                                             if graph_gather else "all_gather_into_tensor of the packed int32 outputs after the graph replay")
             line["strong_scaling"] = strong

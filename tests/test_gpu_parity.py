@@ -195,7 +195,6 @@ def test_predictor_dropin_whole_utterance(predictor, predictor_golden):
     g = predictor_golden
     x = make_audio(g["kind"], g["aseed"], g["samples"])
     assert _same(predictor.predict(audio_data=x.copy()), g["whole"])
-    # int16 ndarray and WAV bytes of the same audio are accepted like the reference accepts them
     out = predictor.predict_batch([x.copy(), x[:20000].copy()])
     assert _same(out[0], g["whole"])
     outs = list(predictor.predict_batches([[x.copy()], [x[:20000].copy(), x.copy()], [x.copy()]]))
@@ -259,3 +258,31 @@ def test_chunk_path_matches_oracle_states(gpu_engines):
         assert (kv[:, :256] - ko).abs().max().item() < 1e-4 and (kv[:, 256:] - vo).abs().max().item() < 1e-4
         cc = st_g.ws["xcat"][5, :14].cpu()
         assert (cc - st_o.cnn_cache[5, 0].t()).abs().max().item() < 1e-4
+
+
+def test_ingest_formats_equal_float_input(predictor, tmp_path):
+    """a1: every input form `MASRPredictor._load_audio` accepts (predict.py:147-164) — int16 / int32 ndarray,
+    stereo ndarray, bytes of a complete WAV file, a path, an open file object — gives exactly the result of the float32
+    samples the reference would convert it to (`_convert_samples_to_float32`, audio.py:532-546: integers scaled by
+    2^-(bits-1), channels averaged)."""
+    import wave
+    x = make_audio("speech", 61, 16000 * 2 + 321)
+    pcm = (np.clip(x, -1, 1) * 32767).astype(np.int16)
+    want = predictor.predict(audio_data=pcm.astype(np.float32) / np.float32(32768.0))
+    assert len(want["text"]) > 0
+    assert predictor.predict(audio_data=pcm) == want                                     # int16 ndarray
+    assert predictor.predict(audio_data=pcm.astype(np.int32) * 65536) == want            # int32 ndarray (same values, 32-bit scale)
+    stereo = np.stack([pcm, pcm], axis=1)
+    assert predictor.predict(audio_data=stereo) == want                                  # [n, 2] -> channel mean
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+    assert predictor.predict(audio_data=path) == want                                    # path
+    with open(path, "rb") as f:
+        assert predictor.predict(audio_data=f.read()) == want                            # bytes of the whole file
+    with open(path, "rb") as f:
+        assert predictor.predict(audio_data=f) == want                                   # file object
+    with wave.open(path, "wb") as w:                                                     # other sample rate: resampling is out of scope -> raises
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(8000); w.writeframes(pcm.tobytes())
+    with pytest.raises(Exception):
+        predictor.predict(audio_data=path)
