@@ -164,6 +164,43 @@ class ConformerEngine:
                 _p(x), _p(ln1[0]), _p(ln1[1]), None if ln2 is None else _p(ln2[0]), None if ln2 is None else _p(ln2[1]),
                 _p(y2), _p(yp[0]), _p(yp[1]), d, M, d, K, 1e-5)
 
+    def time_ffn_gemms(self, ws, M: int, reps: int = 12, iters: int = 5) -> float:
+        """Mean milliseconds per FFN GEMM launch (w_1 and w_2 of block 0 alternating, the shapes and epilogues of the step) with
+        the launches replayed back to back from a CUDA graph and CUDA events around the replay — i.e. without the per-launch
+        host/launch latency that event pairs around single eager launches include (bench.py's roofline leg)."""
+        w, d, tw, L = self.w, self.d, self._tcw, self.w.layers[0]
+        t0p, hidp = ws["t0p"], ws["hidp"]
+        xs = torch.zeros_like(ws["x"])                       # scratch residual stream (the replays keep adding into it)
+        dev = self.device
+
+        def body():
+            for _ in range(reps):
+                self._tc(t0p, d, tw[0, "ffm1"], L.ffm[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+                self._tc(hidp, w.ffn, tw[0, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, xs, d, C=xs, ldc=d, tag="ffn_w2")
+
+        prof, self.prof = self.prof, None
+        n0 = self.launches
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            body()
+        best = float("inf")
+        for _ in range(iters):
+            xs.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        self.launches, self.prof = n0, prof
+        return best / (2 * reps)
+
     def _ln_split(self, x, gb, yp, M):
         self._k("layernorm", "masr_layernorm_split_f16", _p(x), self.d, _p(gb[0]), _p(gb[1]), _p(yp[0]), _p(yp[1]),
                 self.d, M, self.d, 1e-5)
