@@ -676,6 +676,7 @@ class ConformerEngine:
 
     # ---- CUDA-graph replay of the device step (launch-bound otherwise: ~190 launches per step) ------------
     GRAPH_FRAME_QUANTUM = 32      # Fmax is rounded up so ragged batches share graphs; padding never changes results
+    PIPE_DEPTH = 3                # static input sets / pinned staging buffers of the pipelined entry point (results lag PIPE_DEPTH-1 batches)
     STAGE_THREADS = 4             # host threads packing the pinned staging buffer (csrc/stage.cu)
 
     def _graph_for(self, B: int, Fpad: int, use_db: bool, target_db: float, slot: int = 0):
@@ -732,19 +733,19 @@ class ConformerEngine:
     # ---- pipelined batches: host staging + H2D of batch k+1 overlap the device step of batch k ---------------------
     def transcribe_pipelined(self, batches, use_db_normalization: bool = True, target_db: float = -20.0, device_hook=None):
         """Generator over ``batches`` (an iterable of lists of float32 waveforms) yielding one ``GreedyResult`` per batch,
-        in order, each identical to ``transcribe(batch)``.  Two static input sets + two pinned staging buffers: while the
-        CUDA graph of batch k runs on the compute stream, batch k+1 is packed into pinned memory by the native stager and
+        in order, each identical to ``transcribe(batch)``.  PIPE_DEPTH static input sets + pinned staging buffers: while the
+        CUDA graph of batch k runs on the compute stream, batches k+1.. are packed into pinned memory by the native stager and
         copied H2D on a separate copy stream; the packed outputs of batch k come back in one D2H copy.  Results lag the
-        input by one batch.  ``device_hook(out_pack)`` (optional) is called right after each device step is enqueued, with the
+        input by PIPE_DEPTH - 1 batches.  ``device_hook(out_pack)`` (optional) is called right after each device step is enqueued, with the
         packed int32 output tensor still on the device — the place to enqueue the cross-rank token gather (NCCL) of a sharded
         deployment on the same stream."""
         dev = self.device
         comp = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._pipe = [{"pinned": None, "out": None, "staged": torch.cuda.Event(), "done": torch.cuda.Event()} for _ in range(2)]
+            self._pipe = [{"pinned": None, "out": None, "staged": torch.cuda.Event(), "done": torch.cuda.Event()}
+                          for _ in range(self.PIPE_DEPTH)]
         copy = self._copy_stream
-        prev = None
         k = 0
 
         def finish(item):
@@ -764,8 +765,10 @@ class ConformerEngine:
             scores = [greedy_score(psum[b], pcnt[b]) for b in range(B)]
             return GreedyResult(tokens, scores, None, np.asarray(tl, np.int32), st_h)
 
+        from collections import deque
+        pending = deque()                                   # items in flight: at most PIPE_DEPTH - 1 behind the one being staged
         for waves in batches:
-            slot = k & 1
+            slot = k % self.PIPE_DEPTH
             k += 1
             B = len(waves)
             lengths = [int(w.shape[0]) for w in waves]
@@ -790,7 +793,7 @@ class ConformerEngine:
                 waves = [w if (w.dtype == np.float32 and w.flags.c_contiguous) else np.ascontiguousarray(w, np.float32) for w in waves]
                 ptrs = (_lib.C.c_void_p * B)(*[w.ctypes.data for w in waves])
                 lens_c = (_lib.C.c_int64 * B)(*lengths)
-                # the slot's previous batch (k-2) was consumed before its result was yielded: its buffers are free
+                # the slot's previous batch (k - PIPE_DEPTH) was consumed before its result was yielded: its buffers are free
                 call("masr_stage_waves_f32", ptrs, lens_c, B, pin.data_ptr(), g["wave"].data_ptr(), self.STAGE_THREADS,
                      copy.cuda_stream)
                 t0 = (total + 1) // 2 * 2
@@ -814,11 +817,13 @@ class ConformerEngine:
                 P["out"][:pack.numel()].copy_(pack, non_blocking=True)
                 P["done"].record(comp)
                 item = (slot, B, g["T"], tl, g["ws"]["tokens"].shape[1], True)
-            if prev is not None:
-                yield finish(prev)
-            prev = item
-        if prev is not None:
-            yield finish(prev)
+            pending.append(item)
+            # results are handed out PIPE_DEPTH - 1 batches late: the host runs that far ahead of the GPU, which absorbs host
+            # jitter (with a cross-rank collective in every step any rank's hiccup otherwise stalls all ranks: N=8 e2e, r02)
+            while len(pending) >= self.PIPE_DEPTH:
+                yield finish(pending.popleft())
+        while pending:
+            yield finish(pending.popleft())
 
     def prepare_resident(self, waves: Sequence[np.ndarray], use_db: bool = True, target_db: float = -20.0):
         """Stage a batch into the static device buffers of its CUDA graph and return a zero-argument callable
