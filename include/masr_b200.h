@@ -204,6 +204,16 @@ int masr_relpos_attention_tc(const float* Q, int64_t ldq, int64_t q_bstride, con
                              int64_t o_bstride, const int* q_lens, const int* k_lens, int B, int H, int d_k, int max_q,
                              void* stream);
 
+/* masr_relpos_attention_tc on the 5th-generation tensor cores (tcgen05.mma, S and O accumulators in TMEM, K / linear_pos(pe) / V
+ * tiles by TMA, V consumed as an MN-major operand, softmax between the two products inside the kernel): one CTA per
+ * (utterance, head), for utterances of up to 256 frames — max_q <= 256 and every k_lens[b] <= 256 (the batched whole-utterance
+ * path of 10 s audio: T = 248).  Same arguments plus `table_rows` (rows of the P table), same results (fp32-grade). */
+int masr_relpos_attention_tc5(const float* Q, int64_t ldq, int64_t q_bstride, const void* Kh, const void* Kl, const void* Vh,
+                              const void* Vl, int64_t ldk, int64_t k_bstride, const void* Ph, const void* Pl, int64_t ldp,
+                              int64_t table_rows, const float* pos_u, const float* pos_v, float* O, void* Oh, void* Ol,
+                              int64_t ldo, int64_t o_bstride, const int* q_lens, const int* k_lens, int B, int H, int d_k,
+                              int max_q, void* stream);
+
 /* ConvolutionModule middle (masr/model_utils/conformer/convolution.py:121-126): depthwise Conv1d(k)
  * -> LayerNorm(C) -> SiLU.  y[b,t,:] for t < out_rows from g[b, t - lpad + k, :], k < kernel_size;
  * g rows < 0 read pad_vec (NULL = 0), rows >= in_lens[b] read 0.  w [C,k] (reference [C,1,k]).

@@ -48,6 +48,8 @@ SIGNATURES = {
                                   _vp, _vp, _i, _i, _i, _i, _vp],
     "masr_relpos_attention_tc": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
                                  _i64, _vp, _vp, _i, _i, _i, _i, _vp],
+    "masr_relpos_attention_tc5": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
+                                  _i64, _i64, _vp, _vp, _i, _i, _i, _i, _vp],
     "masr_dwconv_ln_silu_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i,
                                 _i, _f, _vp],
     "masr_dwconv_ln_silu_strided_f32": [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i,

@@ -74,6 +74,8 @@ class ConformerEngine:
         # r02 NOT faster than the separate LayerNorm launch — with one tile per CTA the longer epilogue is fully exposed
         # (w_2 34.3 -> 42.6 us vs 6.0 us for the LayerNorm kernel, profiles/r02_ln_fusion.md) — so off unless MASR_FUSE_LN=1.
         self.fuse_ctc = os.environ.get("MASR_FUSE_CTC", "1") != "0"
+        # attention of utterances up to 256 frames on tcgen05 (csrc/attention_tc5.cu); MASR_ATTN=mma keeps the mma.sync kernel
+        self.attn_tc5 = os.environ.get("MASR_ATTN", "tc5") != "mma"
         self.fuse = os.environ.get("MASR_FUSE_LN", "0") == "1"
         self.use_graphs = bool(use_graphs)     # replay the batched device step as one CUDA graph per (B, Fmax) shape
         self._graphs = {}
@@ -146,6 +148,12 @@ class ConformerEngine:
         """qkv fp32 [M,3d] (queries), qkvp its fp16 pair (keys/values) -> outp pair [M,d]."""
         d = self.d
         ph, pl, _ = self._ptab_pair(L)
+        if T <= 256 and self.dk == 64 and self.attn_tc5:
+            # tcgen05 / TMEM / TMA kernel, one CTA per (utterance, head): utterances of up to 256 frames (10 s audio: T = 248)
+            self._k("attention", "masr_relpos_attention_tc5", _p(qkv), 3 * d, T, qkvp[0].data_ptr() + 2 * d, qkvp[1].data_ptr() + 2 * d,
+                    qkvp[0].data_ptr() + 4 * d, qkvp[1].data_ptr() + 4 * d, 3 * d, T, _p(ph), _p(pl), d, ph.shape[0], _p(L.pos_u),
+                    _p(L.pos_v), None, _p(outp[0]), _p(outp[1]), d, T, _p(lens), _p(lens), B, self.h, self.dk, T)
+            return
         self._k("attention", "masr_relpos_attention_tc", _p(qkv), 3 * d, T, qkvp[0].data_ptr() + 2 * d, qkvp[1].data_ptr() + 2 * d,
                 qkvp[0].data_ptr() + 4 * d, qkvp[1].data_ptr() + 4 * d, 3 * d, T, _p(ph), _p(pl), d, _p(L.pos_u), _p(L.pos_v), None,
                 _p(outp[0]), _p(outp[1]), d, T, _p(lens), _p(lens), B, self.h, self.dk, T)

@@ -99,8 +99,8 @@ def test_subsampling_convs(rt):
     assert maxdiff(c2, r2.permute(0, 2, 3, 1)) < 5e-5
 
 
-@pytest.mark.parametrize("fn", ["masr_relpos_attention_f32", "masr_relpos_attention_tc"])
-@pytest.mark.parametrize("lens", [[5], [64, 1], [130, 77, 129], [200], [33, 248]])
+@pytest.mark.parametrize("fn", ["masr_relpos_attention_f32", "masr_relpos_attention_tc", "masr_relpos_attention_tc5"])
+@pytest.mark.parametrize("lens", [[5], [64, 1], [130, 77, 129], [200], [33, 248], [256, 0, 128, 255]])
 def test_relpos_attention(rt, lens, fn):
     g = torch.Generator().manual_seed(sum(lens))
     B, T, H, dk = len(lens), max(lens), 4, 64
@@ -111,7 +111,7 @@ def test_relpos_attention(rt, lens, fn):
     qd, pd, ud, vd = qkv.to(rt.dev), Ptab.to(rt.dev), u.to(rt.dev), v.to(rt.dev)
     ld = torch.tensor(lens, dtype=torch.int32, device=rt.dev)
     out = torch.full((B, T, d), float("nan"), device=rt.dev)
-    if fn == "masr_relpos_attention_tc":
+    if fn in ("masr_relpos_attention_tc", "masr_relpos_attention_tc5"):
         def split(x):
             x = x.contiguous()
             h = torch.empty(x.shape, dtype=torch.float16, device=rt.dev); l = torch.empty_like(h)
@@ -119,13 +119,20 @@ def test_relpos_attention(rt, lens, fn):
             return h, l
         qh, ql = split(qd)
         ph, pl = split(pd)
+        extra = (Ptab.shape[0],) if fn.endswith("tc5") else ()
+        oh = torch.full((B, T, d), float("nan"), dtype=torch.float16, device=rt.dev); ol = torch.full_like(oh, float("nan"))
         rt.call(fn, P(qd), 3 * d, T, qh.data_ptr() + 2 * d, ql.data_ptr() + 2 * d, qh.data_ptr() + 4 * d, ql.data_ptr() + 4 * d,
-                3 * d, T, P(ph), P(pl), d, P(ud), P(vd), P(out), None, None, d, T, P(ld), P(ld), B, H, dk, T, rt.st())
+                3 * d, T, P(ph), P(pl), d, *extra, P(ud), P(vd), P(out), P(oh), P(ol), d, T, P(ld), P(ld), B, H, dk, T, rt.st())
+        torch.cuda.synchronize()
+        assert maxdiff(oh.float() + ol.float() / 2048.0, out) < 2e-6          # the (h,l) pair output reconstructs the fp32 one
     else:
         rt.call(fn, P(qd), 3 * d, T, qd.data_ptr() + 4 * d, qd.data_ptr() + 8 * d, 3 * d, T,
                 P(pd), d, P(ud), P(vd), P(out), None, None, d, T, P(ld), P(ld), B, H, dk, T, rt.st())
     out = out.cpu()
     for b, n in enumerate(lens):
+        if n == 0:
+            assert torch.all(out[b] == 0)
+            continue
         q = qkv[b, :n, :d].view(n, H, dk); k = qkv[b, :n, d:2 * d].view(n, H, dk).transpose(0, 1)
         vv = qkv[b, :n, 2 * d:].view(n, H, dk).transpose(0, 1)
         p = Ptab[:n].view(n, H, dk).transpose(0, 1)
