@@ -11,6 +11,7 @@
 //
 // HBM-bound: 4*(1 + 1) bytes per element, (TW+K-1)/TW read amplification served by L1/L2.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,10 +22,16 @@ namespace masr {
 // halo rows hit L1.  The tap weights sit transposed in shared memory ([k][c], 128-bit reads).  The LayerNorm over the channels
 // of a frame is then a pure warp reduction (two-pass: mean, centred variance) — the first version (thread per channel) needed
 // four block-wide barriers and ~100 instructions per output; this one ~25.
-constexpr int DW_TW = 4;          // frames per warp
+constexpr int DW_TW_DEFAULT = 4;
+constexpr int DW_TW = 4;          // frames per warp (default; MASR_DW_TW=8 selects the 8-frame variant: 2.75x instead of 4.5x input re-reads at k = 15)
+static int dw_tw() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MASR_DW_TW"); v = (e && atoi(e) == 8) ? 8 : (e && atoi(e) == 4) ? 4 : DW_TW_DEFAULT; }
+    return v;
+}
 constexpr int DW_WARPS = 4;       // warps per CTA
 
-template <int KS, int STRIDE, bool AFFINE>
+template <int KS, int STRIDE, bool AFFINE, int TW>
 __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_silu_kernel(const float* __restrict__ g, int64_t ldg,
                                                              int64_t g_bstride, const float* __restrict__ w,
                                                              const float* __restrict__ bias,
@@ -36,11 +43,11 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_silu_kernel(const flo
                                                              float eps) {
     // y[t] = sum_k w[k] * g[t*STRIDE - lpad + k]   (STRIDE 2 = the strided block of the EfficientConformer)
     constexpr int C = 256;
-    constexpr int ROWS = (DW_TW - 1) * STRIDE + KS;          // input rows one warp touches
+    constexpr int ROWS = (TW - 1) * STRIDE + KS;          // input rows one warp touches
     __shared__ __align__(16) float s_w[KS][C];               // tap-major weights
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const int t0 = (blockIdx.x * DW_WARPS + warp) * DW_TW;   // first output frame of this warp
+    const int t0 = (blockIdx.x * DW_WARPS + warp) * TW;   // first output frame of this warp
     // (weights are constants of the model, not outputs of the producer kernel: staged before the dependency wait)
     for (int idx = threadIdx.x; idx < KS * C; idx += DW_WARPS * 32) {
         const int k = idx / C, c = idx - k * C;              // reference layout [C, 1, k]; conflict-free shared stores
@@ -55,9 +62,9 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_silu_kernel(const flo
     const float4 bs0 = ldg_f4(bias + c0), bs1 = ldg_f4(bias + c1);
     float4 pv0 = make_float4(0.f, 0.f, 0.f, 0.f), pv1 = pv0;
     if (pad_vec) { pv0 = ldg_f4(pad_vec + c0); pv1 = ldg_f4(pad_vec + c1); }
-    float4 a0[DW_TW], a1[DW_TW];
+    float4 a0[TW], a1[TW];
 #pragma unroll
-    for (int j = 0; j < DW_TW; ++j) { a0[j] = bs0; a1[j] = bs1; }
+    for (int j = 0; j < TW; ++j) { a0[j] = bs0; a1[j] = bs1; }
     const float* gb = g + (int64_t)b * g_bstride * ldg;
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
@@ -67,7 +74,7 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_silu_kernel(const flo
         else if (tau >= in_len) { v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0; }
         else { v0 = ldg_f4(gb + (int64_t)tau * ldg + c0); v1 = ldg_f4(gb + (int64_t)tau * ldg + c1); }
 #pragma unroll
-        for (int j = 0; j < DW_TW; ++j) {
+        for (int j = 0; j < TW; ++j) {
             const int k = i - j * STRIDE;
             if (k >= 0 && k < KS) {
                 const float4 w0 = *reinterpret_cast<const float4*>(&s_w[k][c0]);
@@ -81,16 +88,16 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_silu_kernel(const flo
     }
     const float4 gg0 = ldg_f4(ln_g + c0), gg1 = ldg_f4(ln_g + c1), bb0 = ldg_f4(ln_b + c0), bb1 = ldg_f4(ln_b + c1);
     // AFFINE: BatchNorm1d(eval) folded by the caller: ln_g = gamma / sqrt(running_var + eps), ln_b = beta - running_mean * ln_g
-    float mean[DW_TW], rstd[DW_TW];
+    float mean[TW], rstd[TW];
 #pragma unroll
-    for (int j = 0; j < DW_TW; ++j) { mean[j] = 0.f; rstd[j] = 1.f; }
+    for (int j = 0; j < TW; ++j) { mean[j] = 0.f; rstd[j] = 1.f; }
     if (!AFFINE) {
         // LayerNorm over the 256 channels of each frame: two-pass statistics, warp-wide
 #pragma unroll
-        for (int j = 0; j < DW_TW; ++j)
+        for (int j = 0; j < TW; ++j)
             mean[j] = warp_sum(((a0[j].x + a0[j].y) + (a0[j].z + a0[j].w)) + ((a1[j].x + a1[j].y) + (a1[j].z + a1[j].w))) * (1.0f / C);
 #pragma unroll
-        for (int j = 0; j < DW_TW; ++j) {
+        for (int j = 0; j < TW; ++j) {
             const float d0 = a0[j].x - mean[j], d1 = a0[j].y - mean[j], d2 = a0[j].z - mean[j], d3 = a0[j].w - mean[j];
             const float d4 = a1[j].x - mean[j], d5 = a1[j].y - mean[j], d6 = a1[j].z - mean[j], d7 = a1[j].w - mean[j];
             const float q = ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
@@ -98,7 +105,7 @@ __global__ void __launch_bounds__(DW_WARPS * 32) dwconv_ln_silu_kernel(const flo
         }
     }
 #pragma unroll
-    for (int j = 0; j < DW_TW; ++j) {
+    for (int j = 0; j < TW; ++j) {
         const int t = t0 + j;
         if (t >= out_rows) break;                            // warp-uniform
         float4 o0, o1;
@@ -150,12 +157,19 @@ extern "C" int masr_dwconv_ln_silu_strided_f32(const float* g, int64_t ldg, int6
     MASR_REQUIRE(C == 256, "masr_dwconv_ln_silu_f32: C=%d unsupported (this build: 256)", C);
     MASR_REQUIRE(ldg % 4 == 0 && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
                  "masr_dwconv_ln_silu_f32: rows must be 16-byte aligned (ldg, ldy multiples of 4)");
-    constexpr int TT = DW_TW * DW_WARPS;
+    const int tw = dw_tw();
+    const int TT = tw * DW_WARPS;
     dim3 grid((out_rows + TT - 1) / TT, B);
     cudaStream_t st = (cudaStream_t)stream;
 #define MASR_DW_LAUNCH(KS, S)                                                                                       \
-    launch_pdl(dwconv_ln_silu_kernel<KS, S, false>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
-               (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps)
+    do {                                                                                                            \
+        if (tw == 8)                                                                                                \
+            launch_pdl(dwconv_ln_silu_kernel<KS, S, false, 8>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
+                       (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps);                      \
+        else                                                                                                        \
+            launch_pdl(dwconv_ln_silu_kernel<KS, S, false, 4>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, ln_gamma, ln_beta, pad_vec, y, \
+                       (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, eps);                      \
+    } while (0)
     MASR_REQUIRE(stride == 1 || stride == 2, "masr_dwconv_ln_silu: stride %d unsupported (1/2)", stride);
     if (stride == 2) {
         MASR_REQUIRE(kernel_size == 15, "masr_dwconv_ln_silu: stride 2 is built for kernel size 15 only");
@@ -189,11 +203,11 @@ extern "C" int masr_dwconv_bn_silu_f32(const float* g, int64_t ldg, int64_t g_bs
     cudaStream_t st = (cudaStream_t)stream;
     switch (kernel_size) {
         case 15:
-            launch_pdl(dwconv_ln_silu_kernel<15, 1, true>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
+            launch_pdl(dwconv_ln_silu_kernel<15, 1, true, DW_TW>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
                 (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, 0.f);
             break;
         case 31:
-            launch_pdl(dwconv_ln_silu_kernel<31, 1, true>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
+            launch_pdl(dwconv_ln_silu_kernel<31, 1, true, DW_TW>, grid, dim3(DW_WARPS * 32), 0, st, g, ldg, g_bstride, w, bias, bn_scale, bn_shift, pad_vec, y,
                 (__half*)yh, (__half*)yl, ldy, y_bstride, in_lens, lpad, out_rows, 0.f);
             break;
         default:
