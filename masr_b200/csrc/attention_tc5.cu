@@ -187,20 +187,36 @@ __global__ void __launch_bounds__(AT_THREADS, 1) relpos_attention_tc5_kernel(con
             tma_2d(&maps.pl, &bars[0], R1 + 3 * 32768, h * AT_D, 0);                // kb 1, l
         }
         {
+            // every thread owns one 16-byte column chunk (c16 = tid & 7: 384 % 8 == 0) of rows tid/8, +48, +96 (the last only for
+            // tid < 256): the positional biases are loaded once, the three rows' query loads are issued together (the r02 capture
+            // showed the dependent load -> add chain of a one-row-at-a-time loop as the kernel's largest stall)
             const float* qsrc = p.Q + ((int64_t)b * p.q_bstride + r0) * p.ldq + h * AT_D;
             const uint32_t base = s_u32(R2);
-            for (int idx = tid; idx < AT_ROWS * 8; idx += AT_THREADS) {
-                const int r = idx >> 3, c16 = idx & 7;
+            const int c16 = tid & 7;
+            const float4 u0 = ldg_f4(p.pos_u + h * AT_D + c16 * 8), u1 = ldg_f4(p.pos_u + h * AT_D + c16 * 8 + 4);
+            const float4 v0 = ldg_f4(p.pos_v + h * AT_D + c16 * 8), v1 = ldg_f4(p.pos_v + h * AT_D + c16 * 8 + 4);
+            float4 qa[3], qb[3];
+#pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int r = (tid >> 3) + it * (AT_THREADS / 8);
+                qa[it] = make_float4(0.f, 0.f, 0.f, 0.f); qb[it] = qa[it];
+                if (r < AT_ROWS && r0 + r < qlen) {
+                    qa[it] = ldg_f4(qsrc + (int64_t)r * p.ldq + c16 * 8);
+                    qb[it] = ldg_f4(qsrc + (int64_t)r * p.ldq + c16 * 8 + 4);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 3; ++it) {
+                const int r = (tid >> 3) + it * (AT_THREADS / 8);
+                if (r >= AT_ROWS) break;
+                const bool ok = r0 + r < qlen;
+                const float4 a0 = qa[it], a1 = qb[it];
                 float qu[8], qv[8];
-                if (r0 + r < qlen) {
-                    const float4 a0 = ldg_f4(qsrc + (int64_t)r * p.ldq + c16 * 8), a1 = ldg_f4(qsrc + (int64_t)r * p.ldq + c16 * 8 + 4);
-                    const float4 u0 = ldg_f4(p.pos_u + h * AT_D + c16 * 8), u1 = ldg_f4(p.pos_u + h * AT_D + c16 * 8 + 4);
-                    const float4 v0 = ldg_f4(p.pos_v + h * AT_D + c16 * 8), v1 = ldg_f4(p.pos_v + h * AT_D + c16 * 8 + 4);
-                    qu[0] = a0.x + u0.x; qu[1] = a0.y + u0.y; qu[2] = a0.z + u0.z; qu[3] = a0.w + u0.w;
-                    qu[4] = a1.x + u1.x; qu[5] = a1.y + u1.y; qu[6] = a1.z + u1.z; qu[7] = a1.w + u1.w;
-                    qv[0] = a0.x + v0.x; qv[1] = a0.y + v0.y; qv[2] = a0.z + v0.z; qv[3] = a0.w + v0.w;
-                    qv[4] = a1.x + v1.x; qv[5] = a1.y + v1.y; qv[6] = a1.z + v1.z; qv[7] = a1.w + v1.w;
-                } else {
+                qu[0] = a0.x + u0.x; qu[1] = a0.y + u0.y; qu[2] = a0.z + u0.z; qu[3] = a0.w + u0.w;
+                qu[4] = a1.x + u1.x; qu[5] = a1.y + u1.y; qu[6] = a1.z + u1.z; qu[7] = a1.w + u1.w;
+                qv[0] = a0.x + v0.x; qv[1] = a0.y + v0.y; qv[2] = a0.z + v0.z; qv[3] = a0.w + v0.w;
+                qv[4] = a1.x + v1.x; qv[5] = a1.y + v1.y; qv[6] = a1.z + v1.z; qv[7] = a1.w + v1.w;
+                if (!ok) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { qu[j] = 0.f; qv[j] = 0.f; }
                 }

@@ -536,11 +536,39 @@ class StreamPool:
     def _reset_hist(self, slots):
         if not hasattr(self, "toks"):
             self.toks = [[] for _ in range(self.S)]
-            self.prev = [None] * self.S
-            self.acc = [np.float32(0.0)] * self.S
-            self.nprob = [0] * self.S
+            self.prev = np.full(self.S, -1, np.int64)          # last frame id per slot (-1: none yet)
+            self.acc = np.zeros(self.S, np.float32)            # left-to-right float32 sum of the non-blank max-probabilities
+            self.nprob = np.zeros(self.S, np.int64)
         for s in slots:
-            self.toks[s], self.prev[s], self.acc[s], self.nprob[s] = [], None, np.float32(0.0), 0
+            self.toks[s] = []
+            self.prev[s], self.acc[s], self.nprob[s] = -1, np.float32(0.0), 0
+
+    def _fold(self, ids_h: np.ndarray, mp_h: np.ndarray, tout: Sequence[int]):
+        """Incremental ``greedy_decoder_chunk`` (ctc_greedy_decoder.py:70-89) for every slot at once: collapse repeats against
+        the previous frame, drop blanks, and keep the score as the reference's left-to-right float32 sum — one vectorised
+        float32 add per frame column (16 columns), so each slot's sum sees its terms in order with float32 rounding at
+        every step, exactly like the scalar loop it replaces (which cost ~0.85 ms per push of 64 streams)."""
+        S, C = ids_h.shape
+        tout = np.asarray(tout, np.int64)
+        if not tout.any():
+            return
+        ids = ids_h.astype(np.int64)
+        valid = np.arange(C)[None, :] < tout[:, None]
+        prev_col = np.concatenate([self.prev[:, None], ids[:, :-1]], axis=1)
+        nonblank = valid & (ids != 0)
+        new_tok = nonblank & (ids != prev_col)
+        acc = self.acc
+        for t in range(C):
+            col = nonblank[:, t]
+            if col.any():
+                acc = np.where(col, (acc + mp_h[:, t]).astype(np.float32), acc)
+        self.acc = acc.astype(np.float32)
+        self.nprob += nonblank.sum(1)
+        for s in np.nonzero(new_tok.any(1))[0]:
+            self.toks[s].extend(ids[s, new_tok[s]].tolist())
+        has = tout > 0
+        last = np.take_along_axis(ids, np.maximum(tout - 1, 0)[:, None], axis=1)[:, 0]
+        self.prev = np.where(has, last, self.prev)
 
     def reset_stream(self, slot: int):
         self.pool.reset(slot)
@@ -630,18 +658,20 @@ class StreamPool:
                 self._grow_ring(need)
             R = self.RING
             # ---- commit: nothing below can fail for a validated slot ----
-            src, dst = [], []
             for j, s in good:
-                nf = frames[j]
-                if nf:
-                    f = np.arange(nf, dtype=np.int64)
-                    src.append(j * Fmax + f)
-                    dst.append(s * R + (self.head[s] + self.count[s] + f) % R)
-                tail = cand[s][FRAME_SHIFT * nf:]
+                tail = cand[s][FRAME_SHIFT * frames[j]:]
                 self.remained[s] = (tail * np.float32(gains[j])).astype(np.float32) if self.use_db else tail
-            if src:                                  # append the new frames of every slot to the ring: one gather + one scatter
-                self.ring.index_copy_(0, self._dev_index(np.concatenate(dst)),
-                                      feats.view(-1, 80).index_select(0, self._dev_index(np.concatenate(src))))
+            # append the new frames of every slot to the ring: one gather + one scatter, index lists built without a per-slot loop
+            gj = np.asarray([j for j, _ in good], np.int64)
+            gs = np.asarray([s for _, s in good], np.int64)
+            nf = np.asarray([frames[j] for j, _ in good], np.int64)
+            if nf.sum() > 0:
+                seg = np.repeat(np.arange(len(good)), nf)
+                off = np.arange(int(nf.sum()), dtype=np.int64) - np.repeat(np.cumsum(nf) - nf, nf)
+                start = np.asarray([self.head[s] + self.count[s] for s in gs], np.int64)
+                src = gj[seg] * Fmax + off
+                dst = gs[seg] * R + (start[seg] + off) % R
+                self.ring.index_copy_(0, self._dev_index(dst), feats.view(-1, 80).index_select(0, self._dev_index(src)))
             for j, s in good:
                 self.count[s] += frames[j]
             live = [s for _, s in good]
@@ -651,29 +681,22 @@ class StreamPool:
             win = np.arange(CHUNK_FRAMES, dtype=np.int64)
             for r in range(rounds):
                 nfr = [0] * S
+                act = [s for s in live if r < len(pending[s])]
                 idx = np.full((S, CHUNK_FRAMES), zero_row, np.int64)
-                for s in live:
-                    if r < len(pending[s]):
-                        cur = pending[s][r]
-                        end = min(cur + CHUNK_FRAMES, self.count[s])
-                        n = end - cur
-                        idx[s, :n] = s * R + (self.head[s] + cur + win[:n]) % R
-                        nfr[s] = n
-                        ends[s] = end
+                if act:
+                    a = np.asarray(act, np.int64)
+                    cur = np.asarray([pending[s][r] for s in act], np.int64)
+                    cnt = np.asarray([self.count[s] for s in act], np.int64)
+                    n = np.minimum(cur + CHUNK_FRAMES, cnt) - cur
+                    hd = np.asarray([self.head[s] for s in act], np.int64)
+                    rows = a[:, None] * R + (hd[:, None] + cur[:, None] + win[None, :]) % R
+                    idx[a] = np.where(win[None, :] < n[:, None], rows, zero_row)
+                    for s, c_, n_ in zip(act, cur, n):
+                        nfr[s] = int(n_)
+                        ends[s] = int(c_ + n_)
                 batch = self.ring.index_select(0, self._dev_index(idx.reshape(-1))).view(S, CHUNK_FRAMES, 80)
                 ids, maxp, tout = self.pool.step(batch, nfr)
-                ids_h, mp_h = ids.cpu().numpy(), maxp.cpu().numpy()
-                for s in live:
-                    prev, acc, toks = self.prev[s], self.acc[s], self.toks[s]
-                    for t in range(tout[s]):
-                        i = int(ids_h[s, t])
-                        if i != 0:
-                            acc = np.float32(acc + mp_h[s, t])
-                            self.nprob[s] += 1
-                            if i != prev:
-                                toks.append(i)
-                        prev = i
-                    self.prev[s], self.acc[s] = prev, acc
+                self._fold(ids.cpu().numpy(), maxp.cpu().numpy(), tout)
             for s in live:
                 if not pending[s]:
                     out[s] = None
@@ -681,7 +704,7 @@ class StreamPool:
                 consumed = ends[s] - CACHED_FEATURE_NUM              # predict.py:330: keep the last 3 frames of the window
                 self.head[s] = (self.head[s] + consumed) % R
                 self.count[s] -= consumed
-                out[s] = {"text": ids_to_text(self.toks[s], self.vocab), "score": greedy_score(self.acc[s], self.nprob[s])}
+                out[s] = {"text": ids_to_text(self.toks[s], self.vocab), "score": greedy_score(self.acc[s], int(self.nprob[s]))}
         if errors and on_error == "raise":
             raise StreamSlotError(errors, out)
         return out
