@@ -125,6 +125,16 @@ int masr_gemm_tc_residual_ln_f16x2(const void* Ah, const void* Al, int64_t lda, 
                                    const float* gamma1, const float* beta1, const float* gamma2, const float* beta2,
                                    float* Y2, void* Yh, void* Yl, int64_t ldx, int M, int N, int K, float eps, void* stream);
 
+/* Post-norm form of the same cluster kernel (Squeezeformer blocks, squeezeformer/encoder.py:412-463):
+ *   X <- LN(residual + alpha * (A.W^T + bias); gamma, beta)   becomes the stream,
+ *   (Yh, Yl) <- ada_scale * X + ada_bias   (the next sub-module's adaptive scale, positionwise.py:57-58; NULL: the pair of X).
+ * Replaces masr_gemm_tc_f16x2(MASR_EPI_RESIDUAL) + masr_layernorm_ada_split_f16 (used by the stream pools, where every launch
+ * saved counts: a chunk step is latency-bound). */
+int masr_gemm_tc_residual_postln_f16x2(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl,
+                                       const float* bias, const float* residual, int64_t ldr, float alpha, float* X,
+                                       const float* gamma, const float* beta, const float* ada_scale, const float* ada_bias,
+                                       void* Yh, void* Yl, int64_t ldx, int M, int N, int K, float eps, void* stream);
+
 /* CTC head without the [M, V] logits: ctc_lo Linear (loss/ctc.py:70) with a GEMM epilogue that keeps, per frame and per
  * 32-column group, (max logit, first argmax, sum exp(x - max)), then a combine kernel -> per-frame argmax id (first
  * maximum, ctc_greedy_decoder.py:21) and max-probability 1 / sum_j exp(x_j - max) (the softmax value of the argmax).

@@ -161,10 +161,12 @@ struct TcParams {
     float* part_s;
     int* part_i;
     float inv_alpha;   // flags bit 4 (residual prefetch): 1 / alpha, exact (alpha is a power of two)
+    const float* ada_s;   // EPI_RESIDUAL_POSTLN: optional per-channel scale / bias applied to the LayerNorm output for the pair
+    const float* ada_b;
 };
 
 // internal epilogue codes (continuing include/masr_b200.h's MASR_EPI_*)
-constexpr int EPI_RESIDUAL_LN = 6, EPI_RESIDUAL_LN2 = 7, EPI_CTC_PARTIAL = 8;
+constexpr int EPI_RESIDUAL_LN = 6, EPI_RESIDUAL_LN2 = 7, EPI_CTC_PARTIAL = 8, EPI_RESIDUAL_POSTLN = 9;
 
 struct TcMaps {
     CUtensorMap a[8];  // GEMM: a[0]=Ah, a[1]=Al.  CONV: a[2*plane + {0:h,1:l}], plane = (kh&1)*2 + (kw&1)
@@ -517,7 +519,20 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
         // (all statistics exchanges come before the first global store of the tile, see ln_apply)
         float o[32];
         ln_apply(L, v, o, p.ln_g + n, p.ln_b + n, p.ln_eps);
-        if (p.epi == EPI_RESIDUAL_LN2) {
+        if (p.epi == EPI_RESIDUAL_POSTLN) {
+            // post-norm block (Squeezeformer): the stream becomes LN(v); the pair carries the next sub-module's adaptive
+            // scale / bias applied to it (squeezeformer/positionwise.py:57-58), or the LayerNorm output itself
+            emit_f32<32, STG>(c, p.C, p.ldc, p.flags, o, n, p.N);
+            if (p.ada_s) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 as = ldg_f4(p.ada_s + n + j), ab = ldg_f4(p.ada_b + n + j);
+                    o[j] = as.x * o[j] + ab.x; o[j + 1] = as.y * o[j + 1] + ab.y;
+                    o[j + 2] = as.z * o[j + 2] + ab.z; o[j + 3] = as.w * o[j + 3] + ab.w;
+                }
+            }
+            emit_pair<32, STG>(c, p.Ch, p.Cl, p.ldc, p.flags, o, n, p.N);
+        } else if (p.epi == EPI_RESIDUAL_LN2) {
             ln_apply(L, o, v, p.ln_g2 + n, p.ln_b2 + n, p.ln_eps);
             emit_f32<32, STG>(c, p.C, p.ldc, p.flags, o, n, p.N);
             if (p.y2) emit_f32<32, STG>(c, p.y2, p.ldc, p.flags, v, n, p.N);
@@ -1095,11 +1110,37 @@ extern "C" int masr_ctc_head_argmax_tc_f16x2(const void* Ah, const void* Al, int
 //   Y2 (optional): fp32 copy of what the pair holds.
 // Launched as clusters of 2 CTAs (the two 128-column tiles of a row block); row statistics cross the pair through
 // distributed shared memory.  Replaces masr_gemm_tc_f16x2(MASR_EPI_RESIDUAL) + masr_layernorm[2]_split_f16.
+static int launch_residual_ln(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, const float* bias,
+                              const float* residual, int64_t ldr, float alpha, float* X, const float* gamma1, const float* beta1,
+                              const float* gamma2, const float* beta2, float* Y2, void* Yh, void* Yl, int64_t ldx, int M, int N,
+                              int K, float eps, int epi_override, const float* ada_s, const float* ada_b, void* stream);
+
 extern "C" int masr_gemm_tc_residual_ln_f16x2(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl,
                                               const float* bias, const float* residual, int64_t ldr, float alpha, float* X,
                                               const float* gamma1, const float* beta1, const float* gamma2, const float* beta2,
                                               float* Y2, void* Yh, void* Yl, int64_t ldx, int M, int N, int K, float eps,
                                               void* stream) {
+    return launch_residual_ln(Ah, Al, lda, Wh, Wl, bias, residual, ldr, alpha, X, gamma1, beta1, gamma2, beta2, Y2, Yh, Yl, ldx, M, N,
+                              K, eps, 0, nullptr, nullptr, stream);
+}
+
+// Post-norm form (Squeezeformer blocks, squeezeformer/encoder.py:412-463): X <- LN(residual + alpha * (A.W^T + bias); gamma, beta)
+// becomes the stream, (Yh, Yl) <- ada_scale * X + ada_bias (the next sub-module's adaptive scale; NULL: the pair of X itself).
+// Same kernel and restrictions as masr_gemm_tc_residual_ln_f16x2; replaces masr_gemm_tc_f16x2(RESIDUAL) + masr_layernorm_ada_split_f16.
+extern "C" int masr_gemm_tc_residual_postln_f16x2(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl,
+                                                  const float* bias, const float* residual, int64_t ldr, float alpha, float* X,
+                                                  const float* gamma, const float* beta, const float* ada_scale,
+                                                  const float* ada_bias, void* Yh, void* Yl, int64_t ldx, int M, int N, int K,
+                                                  float eps, void* stream) {
+    MASR_REQUIRE((ada_scale == nullptr) == (ada_bias == nullptr), "masr_gemm_tc_residual_postln_f16x2: ada_scale/ada_bias must come as a pair");
+    return launch_residual_ln(Ah, Al, lda, Wh, Wl, bias, residual, ldr, alpha, X, gamma, beta, nullptr, nullptr, nullptr, Yh, Yl, ldx, M,
+                              N, K, eps, EPI_RESIDUAL_POSTLN, ada_scale, ada_bias, stream);
+}
+
+static int launch_residual_ln(const void* Ah, const void* Al, int64_t lda, const void* Wh, const void* Wl, const float* bias,
+                              const float* residual, int64_t ldr, float alpha, float* X, const float* gamma1, const float* beta1,
+                              const float* gamma2, const float* beta2, float* Y2, void* Yh, void* Yl, int64_t ldx, int M, int N,
+                              int K, float eps, int epi_override, const float* ada_s, const float* ada_b, void* stream) {
     if (M == 0) return MASR_OK;
     MASR_REQUIRE(Ah && Al && Wh && Wl && residual && X && gamma1 && beta1 && Yh && Yl, "masr_gemm_tc_residual_ln_f16x2: null pointer");
     MASR_REQUIRE((gamma2 == nullptr) == (beta2 == nullptr), "masr_gemm_tc_residual_ln_f16x2: gamma2/beta2 must come as a pair");
@@ -1114,8 +1155,10 @@ extern "C" int masr_gemm_tc_residual_ln_f16x2(const void* Ah, const void* Al, in
     if ((rc = make_map_2d(&maps.w[0], Wh, N, K, K))) return rc;
     if ((rc = make_map_2d(&maps.w[1], Wl, N, K, K))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
-    TcParams p{bias, residual, X, (__half*)Yh, (__half*)Yl, ldr, ldx, M, N, K, gamma2 ? EPI_RESIDUAL_LN2 : EPI_RESIDUAL_LN, alpha, 0, tc_flags() & ~2};
+    TcParams p{bias, residual, X, (__half*)Yh, (__half*)Yl, ldr, ldx, M, N, K,
+               epi_override ? epi_override : (gamma2 ? EPI_RESIDUAL_LN2 : EPI_RESIDUAL_LN), alpha, 0, tc_flags() & ~2};
     p.ln_g = gamma1; p.ln_b = beta1; p.ln_g2 = gamma2; p.ln_b2 = beta2; p.y2 = Y2; p.ln_eps = eps;
+    p.ada_s = ada_s; p.ada_b = ada_b;
     p.flags |= preres_flag(residual, ldr, alpha); p.inv_alpha = 1.0f / alpha;
     const int tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = 2 * tiles_m;

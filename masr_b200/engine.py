@@ -172,6 +172,14 @@ class ConformerEngine:
                 _p(x), _p(ln1[0]), _p(ln1[1]), None if ln2 is None else _p(ln2[0]), None if ln2 is None else _p(ln2[1]),
                 _p(y2), _p(yp[0]), _p(yp[1]), d, M, d, K, 1e-5)
 
+    def _tc_postln(self, A, lda, W, bias, M, K, x, ln, ada, yp, alpha=1.0, tag="gemm"):
+        """Post-norm blocks (Squeezeformer): x <- LN(x + alpha * (A.W^T + bias)); yp <- ada_scale * x + ada_bias (or pair(x)),
+        one kernel (masr_gemm_tc_residual_postln_f16x2)."""
+        d = self.d
+        self._k(tag, "masr_gemm_tc_residual_postln_f16x2", _p(A[0]), _p(A[1]), lda, _p(W[0]), _p(W[1]), _p(bias), _p(x), d, alpha,
+                _p(x), _p(ln[0]), _p(ln[1]), None if ada is None else _p(ada[0]), None if ada is None else _p(ada[1]),
+                _p(yp[0]), _p(yp[1]), d, M, d, K, 1e-5)
+
     def time_ffn_gemms(self, ws, M: int, reps: int = 12, iters: int = 5) -> float:
         """Mean milliseconds per FFN GEMM launch (w_1 and w_2 of block 0 alternating, the shapes and epilogues of the step) with
         the launches replayed back to back from a CUDA graph and CUDA events around the replay — i.e. without the per-launch

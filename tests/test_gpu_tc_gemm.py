@@ -194,3 +194,28 @@ def test_ctc_head_fused_argmax(rt, M, V, K):
     assert (ids1.cpu() == V - 1).sum() == 0 and (ids1.cpu() == 37).sum() == 0      # ties resolve to the first index
     assert (mp0 - mp1).abs().max().item() < 1e-6
     assert (mp1.cpu().double() - torch.softmax(ref, 1).max(1).values).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("M,K,ada", [(1024, 2048, True), (16, 256, True), (200, 256, False)])
+def test_residual_postln_epilogue(rt, M, K, ada):
+    """masr_gemm_tc_residual_postln_f16x2 (Squeezeformer post-norm blocks, used by the stream pools): the stream becomes
+    LN(residual + A.W^T + bias), the operand pair carries the adaptive scale / bias of the next sub-module."""
+    N = 256
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.randn(M, K, generator=g); W = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g); R = torch.randn(M, N, generator=g) * 2 - 0.3
+    ga, be = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1
+    a_s, a_b = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.2
+    Ad, Wd, bd, gd, bed, asd, abd = (t.to(rt.dev) for t in (A, W, b, ga, be, a_s, a_b))
+    Ah, Al = split(rt, Ad)
+    Wh, Wl = split(rt, Wd)
+    X = R.clone().to(rt.dev)
+    Yh = torch.zeros(M, N, dtype=torch.float16, device=rt.dev); Yl = torch.zeros_like(Yh)
+    rt.call("masr_gemm_tc_residual_postln_f16x2", P(Ah), P(Al), K, P(Wh), P(Wl), P(bd), P(X), N, 1.0, P(X), P(gd), P(bed),
+            P(asd) if ada else None, P(abd) if ada else None, P(Yh), P(Yl), N, M, N, K, 1e-5, rt.st())
+    torch.cuda.synchronize()
+    want_x = F.layer_norm(R + F.linear(A, W, b), (N,), ga, be, 1e-5)
+    want_y = a_s * want_x + a_b if ada else want_x
+    tol = 2e-5 * max(1.0, math.sqrt(K / 256))
+    assert (X.cpu() - want_x).abs().max().item() < tol
+    assert ((Yh.float() + Yl.float() / 2048.0).cpu() - want_y).abs().max().item() < 2 * tol
