@@ -50,11 +50,11 @@ class _PoolBase:
         self.feats_in = torch.zeros(n_slots, CHUNK_FRAMES, 80, device=dev, dtype=torch.float32)
         self.lens_host = [0] * n_slots
         self.use_graph = bool(use_graph) and eng.use_graphs
-        # a chunk step is M = slots x 16 rows: every kernel sits at its launch / latency floor, so here (unlike the
-        # whole-utterance path) folding the LayerNorm into the preceding residual projection pays — 4 launches
-        # per block fewer.  MASR_POOL_FUSE_LN=0 keeps the separate kernels.
+        # LayerNorm folded into the preceding residual projection (cluster kernel, 4 launches per block fewer): measured r02
+        # SLOWER here too (64 streams: 3.77 vs 3.51-3.59 ms per push, 547 vs 710 launches) — the cluster launch + DSMEM exchange
+        # cost more than the ~2 us LayerNorm launch they replace at M = 1024.  Off unless MASR_POOL_FUSE_LN=1 (tests cover both).
         import os
-        self.fuse_ln = os.environ.get("MASR_POOL_FUSE_LN", "1") != "0" and eng.d == 256
+        self.fuse_ln = os.environ.get("MASR_POOL_FUSE_LN", "0") == "1" and eng.d == 256
         self._graph = None
         self._graph_launches = 0
         self._warm = False
