@@ -71,11 +71,13 @@ __global__ void __launch_bounds__(256) conv1_cmvn_relu_kernel(const float* __res
                 // (t,f)-parity planes [4][B][TH][20][C] for the stride-2 implicit GEMM (tc_gemm.cu)
                 const int plane = (t & 1) * 2 + (f & 1);
                 const int64_t idx = ((((int64_t)plane * B + b) * TH + (t >> 1)) * 20 + (f >> 1)) * C + co;
-                __half hh[8], ll[8];
+                // packed conversions (cvt.rn.f16x2.f32: two values per instruction; same round-to-nearest results as the scalar form)
+                __half2 hh[4], ll[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    hh[j] = __float2half_rn(acc[j]);
-                    ll[j] = __float2half_rn((acc[j] - __half2float(hh[j])) * 2048.0f);
+                for (int j = 0; j < 4; ++j) {
+                    hh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+                    const float2 hf = __half22float2(hh[j]);
+                    ll[j] = __floats2half2_rn((acc[2 * j] - hf.x) * 2048.0f, (acc[2 * j + 1] - hf.y) * 2048.0f);
                 }
                 *reinterpret_cast<uint4*>(ph + idx) = *reinterpret_cast<const uint4*>(hh);
                 *reinterpret_cast<uint4*>(pl + idx) = *reinterpret_cast<const uint4*>(ll);
