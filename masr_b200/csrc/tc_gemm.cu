@@ -20,6 +20,10 @@
 //            through shared memory -> row-contiguous 128-bit stores (fp32 and/or the fp16 (h,l) pair the next GEMM consumes)
 //   smem ring of 3 x 64 KB stages with full/empty mbarriers; tcgen05.commit releases slots and signals the epilogue.
 //   Launched with programmatic dependent launch: the prologue overlaps the producer kernel's tail.
+// Round-2 additions: residual epilogues fetch the residual at tile start into the running sum (flags bit 4);
+// EPI_CTC_PARTIAL keeps per (row, 32 columns) softmax partials instead of logits (+ ctc_partial_combine_kernel);
+// the LNC variant (clusters of 2 CTAs) fuses the LayerNorm(s) that follow a residual projection, row statistics over DSMEM
+// (pre-norm LN / LN2 and the Squeezeformer's post-norm + adaptive scale) — measured, not the default.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -856,10 +860,9 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
 
 // ---- CTC head: combine the per-(row, 32-column group) softmax partials of the EPI_CTC_PARTIAL epilogue -------------------------
 // A CTA handles 32 frames: lane = frame (coalesced [group][row] reads), the 4 warps take interleaved quarters of the groups
-// (8 independent loads in flight per thread), online max / sum-exp merge per thread, then the four partials of a frame
-// are merged in ascending column order of their FIRST group... order only matters for ties: the candidate with the
-// larger max wins, equal maxima resolve to the lower column index (numpy's argmax, ctc_greedy_decoder.py:21).
-// max-prob = 1 / sum_j exp(x_j - max).
+// (8 independent loads in flight per thread) with an online max / sum-exp merge per thread (ascending groups, strict >, so a
+// thread keeps the FIRST maximum of its groups); the four partials of a frame are then merged: the larger maximum wins, equal
+// maxima resolve to the lower column index (numpy's argmax, ctc_greedy_decoder.py:21).  max-prob = 1 / sum_j exp(x_j - max).
 __global__ void __launch_bounds__(128) ctc_partial_combine_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
                                                                   const int* __restrict__ pi, int M, int groups,
                                                                   int* __restrict__ ids, float* __restrict__ maxp) {
