@@ -39,6 +39,15 @@ constexpr int TBM = 128, TBN = 128, TBK = 64;
 constexpr int TSTAGES = 3;
 constexpr int TILE_BYTES = TBM * TBK * 2;              // 16 KB: one operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;            // Ah, Al, Wh, Wl
+// PAIR kernels (cta_group::2, a 256 x 128 tile per pair of CTAs): a CTA stages its own 128 A rows and HALF of the W tile
+// (64 of the 128 output columns; the tensor cores of both SMs read both halves) -> 48 KB per K-block, 4 stages
+template <bool PAIR> struct RingCfg {
+    static constexpr int STAGES = PAIR ? 4 : TSTAGES;
+    static constexpr int W_BYTES = PAIR ? TILE_BYTES / 2 : TILE_BYTES;
+    static constexpr int BYTES = 2 * TILE_BYTES + 2 * W_BYTES;
+};
+constexpr int MAX_STAGES = 4;
+static_assert(RingCfg<true>::STAGES * RingCfg<true>::BYTES == TSTAGES * STAGE_BYTES, "both rings take 192 KB");
 constexpr int EPI_STAGE_TOTAL = 32768;                 // epilogue store staging, split evenly over the epilogue warps
 constexpr int tc_threads(int ew) { return 64 + 32 * ew; }   // TMA warp + MMA warp + EW epilogue warps
 constexpr uint32_t TMEM_COLS = 512;                    // 2 x main (ping-pong) + correction accumulator, 128 fp32 columns each (384 -> 512)
@@ -104,6 +113,39 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- cta_group::2 forms (PAIR kernels): issued by the leader CTA (cluster rank 0) for both SMs of the pair ----
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier at this CTA-relative address in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// TMA into this CTA's shared memory, transaction bytes reported to an mbarrier of the pair's leader (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster, void* smem_dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_cluster, void* smem_dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -130,6 +172,32 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 }
 
 // fp32 -> (h, l) with l pre-scaled by 2^11
+// packed fp32 arithmetic (Blackwell f32x2: two independent IEEE round-to-nearest operations per issue slot; the results are
+// bit-identical to the scalar forms).  The epilogues of the K <= 256 GEMMs are bound by issue slots and pipe time, not by data.
+#ifdef MASR_TC_SCALAR_EPI      // A/B builds only: the scalar forms
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) { d0 = fmaf(a0, b0, c0); d1 = fmaf(a1, b1, c1); }
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) { d0 = a0 + b0; d1 = a1 + b1; }
+__device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, float b0, float b1) { d0 = a0 - b0; d1 = a1 - b1; }
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) { d0 = a0 * b0; d1 = a1 * b1; }
+#else
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\t"
+        "fma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tsub.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmul.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+#endif
 __device__ __forceinline__ void split_f16(float x, __half& h, __half& l) {
     h = __float2half_rn(x);
     l = __float2half_rn((x - __half2float(h)) * kLoScale);
@@ -138,7 +206,10 @@ __device__ __forceinline__ void split_f16(float x, __half& h, __half& l) {
 __device__ __forceinline__ void split_f16x2(float x0, float x1, __half2& h, __half2& l) {
     h = __floats2half2_rn(x0, x1);
     const float2 hf = __half22float2(h);
-    l = __floats2half2_rn((x0 - hf.x) * kLoScale, (x1 - hf.y) * kLoScale);
+    float d0, d1;
+    sub2(d0, d1, x0, x1, hf.x, hf.y);
+    mul2(d0, d1, d0, d1, kLoScale, kLoScale);
+    l = __floats2half2_rn(d0, d1);
 }
 struct TcParams {
     const float* bias;
@@ -469,11 +540,15 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
             for (int j = 0; j < 32; j += 8) {
                 float e[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) e[k] = ex2_approx(v[j + k] * -1.4426950408889634f);
+                for (int k = 0; k < 8; k += 2) mul2(e[k], e[k + 1], v[j + k], v[j + k + 1], -1.4426950408889634f, -1.4426950408889634f);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) e[k] = rcp_approx(1.0f + e[k]);
+                for (int k = 0; k < 8; ++k) e[k] = ex2_approx(e[k]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[j + k] *= e[k];
+                for (int k = 0; k < 8; k += 2) add2(e[k], e[k + 1], e[k], e[k + 1], 1.0f, 1.0f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = rcp_approx(e[k]);
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) mul2(v[j + k], v[j + k + 1], v[j + k], v[j + k + 1], e[k], e[k + 1]);
             }
             break;
         case MASR_EPI_BIAS_RELU:
@@ -565,18 +640,27 @@ __device__ __forceinline__ void store_chunk(const TcParams& p, const EpiCtx& c, 
 constexpr int LN_RED_BYTES = 2 * 2 * 4 * 128 * 8;     // red[buffer][source CTA][column group][row] (mean, M2)
 __host__ __device__ constexpr int epi_stage_bytes(int ew, bool lnc) { return lnc ? 1024 * ew : EPI_STAGE_TOTAL; }
 
-template <bool CONV, int EW, bool LNC>
+// PAIR: the cta_group::2 form.  A cluster of 2 CTAs owns a 256 x 128 tile: CTA r stages A rows [128 r, 128 r + 128) and W rows
+// (output columns) [64 r, 64 r + 64) of every K-block in its own shared memory, all transaction bytes land on the LEADER's
+// (rank 0) full barrier, the leader's MMA thread issues M = 256 MMAs that read both CTAs' shared memory and write 128
+// accumulator rows into each CTA's tensor memory, and its commits arrive (multicast) on the empty / accumulator-full barriers
+// of both CTAs.  Each CTA's epilogue warps drain their own TMEM and release the accumulators on the leader's barriers.
+// Per SM and K-block that is 48 KB of TMA writes + 72 KB of operand reads instead of 64 + 96 KB: the 128 x 128 single-CTA
+// mainloop is bound by the 128 B/clk shared-memory port and the L2 -> SM fabric (profiles/r02_gemm_prof_summary.md).
+template <bool CONV, int EW, bool LNC, bool PAIR = false>
 __global__ void __launch_bounds__(tc_threads(EW), 1)
 tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, int tiles_n, int tiles_t) {
     static_assert(!LNC || (EW == 16 && !CONV), "the LayerNorm epilogue needs one 32-column chunk per epilogue warp");
+    static_assert(!(LNC && PAIR), "the LayerNorm-fused kernel pairs CTAs along N, the cta_group::2 kernel along M");
+    using R = RingCfg<PAIR>;
     constexpr int EPI_BYTES = epi_stage_bytes(EW, LNC);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi_stage = smem + TSTAGES * STAGE_BYTES;                // EPI_BYTES / EW per warp (see staged_store)
+    uint8_t* epi_stage = smem + R::STAGES * R::BYTES;                 // EPI_BYTES / EW per warp (see staged_store)
     uint8_t* ln_red = epi_stage + EPI_BYTES;                          // LNC only
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ln_red + (LNC ? LN_RED_BYTES : 0));
-    uint64_t* empty_bar = full_bar + TSTAGES;
-    uint64_t* main_full = empty_bar + TSTAGES;     // [2]
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* main_full = empty_bar + MAX_STAGES;  // [2]
     uint64_t* main_empty = main_full + 2;          // [2]
     uint64_t* corr_full = main_empty + 2;          // [2]
     uint64_t* corr_empty = corr_full + 2;          // [2]
@@ -585,23 +669,45 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.K / TBK;
+    uint32_t crank = 0;                                               // PAIR: rank in the CTA pair (0 = leader)
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // K <= 256 without a prefetched residual: the "direct" epilogue (TMEM -> registers -> stores, no running sum).
+    // (Tried and dropped, tools/step_ab.py: two groups of 8 epilogue warps taking alternate tiles, 64 columns per warp, to
+    // overlap the FP32 / MUFU / store phases that 16 warps on one tile run in lockstep -> step +1.4 %, not faster.)
+    const bool pre_res_k = (LNC || p.epi == MASR_EPI_RESIDUAL) && (p.flags & 16);
+    const bool direct = nkb <= CHUNK_KB && !pre_res_k;
+    const int acc_release = EW * (PAIR ? 2 : 1);                      // arrivals that hand an accumulator buffer back
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.a[0]); tma_prefetch_desc(&maps.a[1]); tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
-        for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < R::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], EW);
-            mbar_init(&corr_full[s], 1); mbar_init(&corr_empty[s], EW);
+            // PAIR: the accumulator-empty barriers that count are the leader's; the epilogue warps of both CTAs arrive there
+            mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], acc_release);
+            mbar_init(&corr_full[s], 1); mbar_init(&corr_empty[s], acc_release);
             if (LNC) mbar_init(&ln_bar[s], 2 * EW);                  // one arrival per epilogue warp of both CTAs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {     // collective over the pair: the same warp of both CTAs, the same slot address
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    // PAIR: nobody may signal a barrier of the other CTA (TMA transaction bytes, commits, accumulator releases) before that
+    // CTA has initialised it
+    if (PAIR) {
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    }
     // the peer CTA must have initialised its barriers before anybody arrives on them remotely: arrive here, wait (long
     // since complete) right before the first exchange / after the producer and MMA loops
     if (LNC) asm volatile("barrier.cluster.arrive.release;" ::: "memory");
@@ -612,27 +718,50 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     pdl_wait();
     pdl_launch_dependents();
 
-    // tile -> coordinates
+    // tile -> coordinates.  PAIR: `tile` numbers 256-row (CONV: 12 time rows) pair tiles, this CTA owns half `crank` of it;
+    // a half that lies beyond M / T2 loads zeros and stores nothing
     auto decode = [&](int tile, int& n0, int& m0, int& t0, int& b) {
         const int nt = tile % tiles_n;
         const int rest = tile / tiles_n;
         n0 = nt * TBN;
-        if (CONV) { t0 = (rest % tiles_t) * CONV_TR; b = rest / tiles_t; m0 = 0; }
-        else { m0 = rest * TBM; t0 = 0; b = 0; }
+        if (CONV) { t0 = ((rest % tiles_t) * (PAIR ? 2 : 1) + (int)crank) * CONV_TR; b = rest / tiles_t; m0 = 0; }
+        else { m0 = (rest * (PAIR ? 2 : 1) + (int)crank) * TBM; t0 = 0; b = 0; }
     };
 
     if (warp == 0) {
         if (elect_one_sync()) {
             constexpr uint32_t a_bytes = CONV ? CONV_ROWS * TBK * 2 : TILE_BYTES;
+            constexpr uint32_t tx_bytes = (2 * a_bytes + 2 * R::W_BYTES) * (PAIR ? 2 : 1);   // PAIR: both CTAs' boxes
             uint32_t kg = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 int n0, m0, t0, b;
                 decode(tile, n0, m0, t0, b);
                 for (int kb = 0; kb < nkb; ++kb, ++kg) {
-                    const uint32_t s = kg % TSTAGES;
-                    mbar_wait(&empty_bar[s], ((kg / TSTAGES) & 1) ^ 1);
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[s], 2 * a_bytes + 2 * TILE_BYTES);
+                    const uint32_t s = kg % R::STAGES;
+                    mbar_wait(&empty_bar[s], ((kg / R::STAGES) & 1) ^ 1);
+                    uint8_t* st = smem + s * R::BYTES;
+                    if (p.flags & 32) {      // profiling switch (tools/gemm_bound_probe.py): no loads, the MMAs run on stale tiles
+                        if (!PAIR || crank == 0) mbar_arrive(&full_bar[s]);
+                        continue;
+                    }
+                    if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
+                    if (PAIR) {
+                        const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);     // the leader's barrier
+                        const int wrow = n0 + (int)crank * (TBN / 2);
+                        if (CONV) {
+                            const int tap = kb >> 2, cj = kb & 3;
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            const int plane = (kh & 1) * 2 + (kw & 1);
+                            tma_load_4d_pair(&maps.a[2 * plane], fb, st, cj * TBK, kw >> 1, t0 + (kh >> 1), b);
+                            tma_load_4d_pair(&maps.a[2 * plane + 1], fb, st + TILE_BYTES, cj * TBK, kw >> 1, t0 + (kh >> 1), b);
+                        } else {
+                            tma_load_2d_pair(&maps.a[0], fb, st, kb * TBK, m0);
+                            tma_load_2d_pair(&maps.a[1], fb, st + TILE_BYTES, kb * TBK, m0);
+                        }
+                        tma_load_2d_pair(&maps.w[0], fb, st + 2 * TILE_BYTES, kb * TBK, wrow);      // box: 64 rows
+                        tma_load_2d_pair(&maps.w[1], fb, st + 2 * TILE_BYTES + R::W_BYTES, kb * TBK, wrow);
+                        continue;
+                    }
                     if (CONV) {
                         const int tap = kb >> 2, cj = kb & 3;       // K index = tap*256 + cj*64  (C = 256)
                         const int kh = tap / 3, kw = tap - kh * 3;
@@ -650,16 +779,20 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
         }
         if (LNC) asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
     } else if (warp == 1) {
-        if (elect_one_sync()) {
-            // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 @17, M>>4 @24
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        if ((!PAIR || crank == 0) && elect_one_sync()) {
+            // instruction descriptor: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 @17, M>>4 @24 (PAIR: M = 256 over two CTAs)
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TBM : TBM) >> 4) << 24);
+            auto mma = [](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+                if (PAIR) umma_f16_pair(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc);
+            };
+            auto commit = [](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             uint32_t kg = 0, cg = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++tl) {
                 mbar_wait(&corr_empty[tl & 1], ((tl >> 1) & 1) ^ 1);    // epilogue has read corr of tile tl-2
                 tc_fence_after();
                 const uint32_t d_corr = tmem_base + 2 * TBN + (tl & 1) * TBN;
                 for (int kb = 0; kb < nkb; ++kb, ++kg) {
-                    const uint32_t s = kg % TSTAGES;
+                    const uint32_t s = kg % R::STAGES;
                     const bool first = (kb % CHUNK_KB) == 0;
                     const bool last = (kb % CHUNK_KB) == CHUNK_KB - 1 || kb == nkb - 1;
                     if (first) {
@@ -667,22 +800,23 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
                         tc_fence_after();
                     }
                     const uint32_t d_main = tmem_base + (cg & 1) * TBN;
-                    mbar_wait(&full_bar[s], (kg / TSTAGES) & 1);
+                    mbar_wait(&full_bar[s], (kg / R::STAGES) & 1);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + s * R::BYTES);
                     const uint64_t dAh = umma_desc_k_sw128(sa), dAl = umma_desc_k_sw128(sa + TILE_BYTES);
-                    const uint64_t dWh = umma_desc_k_sw128(sa + 2 * TILE_BYTES), dWl = umma_desc_k_sw128(sa + 3 * TILE_BYTES);
+                    const uint64_t dWh = umma_desc_k_sw128(sa + 2 * TILE_BYTES), dWl = umma_desc_k_sw128(sa + 2 * TILE_BYTES + R::W_BYTES);
+                    if (!(p.flags & 64))     // profiling switch: loads only, no MMAs
 #pragma unroll
                     for (int ks = 0; ks < TBK / 16; ++ks) {
                         const uint64_t adv = (uint64_t)(ks * 2);      // 16 halves = 32 B = 2 x 16-byte units
-                        umma_f16(d_main, dAh + adv, dWh + adv, idesc, (first && ks == 0) ? 0u : 1u);
-                        umma_f16(d_corr, dAh + adv, dWl + adv, idesc, (kb | ks) ? 1u : 0u);
-                        umma_f16(d_corr, dAl + adv, dWh + adv, idesc, 1u);
+                        mma(d_main, dAh + adv, dWh + adv, (first && ks == 0) ? 0u : 1u);
+                        mma(d_corr, dAh + adv, dWl + adv, (kb | ks) ? 1u : 0u);
+                        mma(d_corr, dAl + adv, dWh + adv, 1u);
                     }
-                    umma_commit(&empty_bar[s]);                        // slot reusable once these MMAs retire
-                    if (last) { umma_commit(&main_full[cg & 1]); ++cg; }
+                    commit(&empty_bar[s]);                             // slot reusable once these MMAs retire
+                    if (last) { commit(&main_full[cg & 1]); ++cg; }
                 }
-                umma_commit(&corr_full[tl & 1]);                       // whole tile (incl. corrections) complete
+                commit(&corr_full[tl & 1]);                            // whole tile (incl. corrections) complete
             }
         }
         if (LNC) asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
@@ -707,19 +841,12 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lnx.bar_peer) : "r"(lnx.bar), "r"(rank ^ 1u));
             asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
         }
-        uint32_t cg = 0, tl = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-            int n0, m0, t0, b;
-            decode(tile, n0, m0, t0, b);
-            const int nw = n0 + cgrp * CW;                             // first column of this warp
-            // bias of the warp's columns: lane l keeps columns l (and 32+l), broadcast by shuffle below;
-            // fetched before the accumulator wait so its latency is hidden
-            float bias0 = 0.f, bias1 = 0.f;
-            if (p.bias != nullptr) {
-                if (nw + lane < p.N) bias0 = __ldg(p.bias + nw + lane);
-                if (NCH > 1 && nw + 32 + lane < p.N) bias1 = __ldg(p.bias + nw + 32 + lane);
-            }
-            // row mapping: the warp's 32 tile rows are 32 consecutive output rows in both modes
+        // accumulator release: PAIR -> the leader's barrier (a shared::cluster address; the leader's own for rank 0)
+        auto release = [&](uint64_t* bar) {
+            if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0)); else mbar_arrive(bar);
+        };
+        // row mapping: the warp's 32 tile rows are 32 consecutive output rows in both modes
+        auto map_rows = [&](int m0, int t0, int b) {
             if (CONV) {
                 // tile row r = ti*19 + f  ->  output row (b*T2 + t0)*19 + r, for r < 114 and t0 + ti < T2
                 const int rows = min(CONV_ROWS, (p.conv_T2 - t0) * CONV_W2);
@@ -729,41 +856,76 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
                 ctx.row0 = (int64_t)m0 + q * 32;
                 ctx.nvalid = max(0, min(32, p.M - (m0 + q * 32)));
             }
+        };
+        // direct epilogue of one 32-column slice (tile columns [col, col + 32) = output columns [n, n + 32)) of accumulator
+        // buffer `buf`: v = main + 2^-11 * correction + bias in packed fp32 pairs, the bias from warp-uniform 128-bit loads
+        // (one broadcast transaction each, L1 hits after bias_prefetch) instead of 32 shuffles
+        const uint32_t lane_tm = tmem_base + ((uint32_t)(q * 32) << 16);
+        auto bias_prefetch = [&](int nw, int cols) {
+            if (p.bias != nullptr && lane * 32 < cols && nw + lane * 32 < p.N)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + nw + lane * 32));
+        };
+        auto direct_slice = [&](uint32_t col, int n, bool last, uint32_t buf) {
+            uint32_t r[32], rc[32];
+            tmem_ld32(lane_tm + buf * TBN + col, r);
+            tmem_ld32(lane_tm + 2 * TBN + buf * TBN + col, rc);
+            tmem_ld_wait();
+            if (last) {                                           // TMEM released: the rest runs from registers
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { release(&main_empty[buf]); release(&corr_empty[buf]); }
+            }
+            if (n >= p.N) return;                                  // warp-uniform
+            float v[32];
+            if (p.bias != nullptr && n + 31 < p.N && (reinterpret_cast<uintptr_t>(p.bias + n) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bb = ldg_f4(p.bias + n + j);
+                    fma2(v[j], v[j + 1], __uint_as_float(rc[j]), __uint_as_float(rc[j + 1]), kLoInv, kLoInv, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                    fma2(v[j + 2], v[j + 3], __uint_as_float(rc[j + 2]), __uint_as_float(rc[j + 3]), kLoInv, kLoInv, __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    add2(v[j], v[j + 1], v[j], v[j + 1], bb.x, bb.y);
+                    add2(v[j + 2], v[j + 3], v[j + 2], v[j + 3], bb.z, bb.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float bj = (p.bias != nullptr && n + j < p.N) ? __ldg(p.bias + n + j) : 0.f;
+                    v[j] = fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])) + bj;
+                }
+            }
+            store_chunk<STG, LNC>(p, ctx, v, n, lnx);
+        };
+        uint32_t cg = 0, tl = 0;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++tl) {
+            int n0, m0, t0, b;
+            decode(tile, n0, m0, t0, b);
+            const int nw = n0 + cgrp * CW;                             // first column of this warp
+            map_rows(m0, t0, b);
+            if (direct) {
+                // K <= 256: main and correction accumulators complete together (one chunk per tile: cg == tl); go straight
+                // from TMEM to the stores 32 columns at a time (no 64-register running sum, so the activations keep their ILP)
+                bias_prefetch(nw, CW);
+                mbar_wait(&main_full[tl & 1], (tl >> 1) & 1);
+                mbar_wait(&corr_full[tl & 1], (tl >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < NCH; ++cc) direct_slice((uint32_t)(cgrp * CW + cc * 32), nw + cc * 32, cc == NCH - 1, tl & 1);
+                ++cg;
+                continue;
+            }
+            // bias of the warp's columns: lane l keeps columns l (and 32+l), broadcast by shuffle below;
+            // fetched before the accumulator wait so its latency is hidden
+            float bias0 = 0.f, bias1 = 0.f;
+            if (p.bias != nullptr) {
+                if (nw + lane < p.N) bias0 = __ldg(p.bias + nw + lane);
+                if (NCH > 1 && nw + 32 + lane < p.N) bias1 = __ldg(p.bias + nw + 32 + lane);
+            }
             // Residual epilogues (flags bit 4): this thread's residual values are fetched NOW, before the first accumulator
             // is ready, and seed the running sum as residual / alpha (alpha is a power of two: exact), so the finished row is
             // alpha * (sum + bias).  ncu r02: loaded after the last MMA, the row-strided residual read (8 x LDG.128 per
             // thread, 32 lines per instruction) was more than half of the exposed epilogue of the single-tile-per-CTA GEMMs
             // (w_2: ~11 of 34 us).
             const bool pre_res = (LNC || p.epi == MASR_EPI_RESIDUAL) && (p.flags & 16);
-            if (nchunks == 1 && !pre_res) {
-                // K <= 256: main and correction accumulators complete together; go straight from TMEM to the
-                // stores 32 columns at a time (no 64-register running sum, so the activations keep their ILP)
-                mbar_wait(&main_full[cg & 1], (cg >> 1) & 1);
-                mbar_wait(&corr_full[tl & 1], (tl >> 1) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < NCH; ++cc) {
-                    uint32_t r[32], rc[32];
-                    tmem_ld32(lane_base + (cg & 1) * TBN + cc * 32, r);
-                    tmem_ld32(lane_base + 2 * TBN + (tl & 1) * TBN + cc * 32, rc);
-                    tmem_ld_wait();
-                    if (cc == NCH - 1) {                          // TMEM released: the rest runs from registers
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { mbar_arrive(&main_empty[cg & 1]); mbar_arrive(&corr_empty[tl & 1]); }
-                    }
-                    const int n = nw + cc * 32;
-                    if (n >= p.N) continue;                            // warp-uniform
-                    float v[32];
-                    const float bsrc = cc ? bias1 : bias0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        v[j] = fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(r[j])) + __shfl_sync(0xffffffffu, bsrc, j);
-                    store_chunk<STG, LNC>(p, ctx, v, n, lnx);
-                }
-                ++cg;
-                continue;
-            }
             float acc[CW];
 #pragma unroll
             for (int j = 0; j < CW; ++j) acc[j] = 0.f;
@@ -799,7 +961,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&main_empty[cg & 1]);
+                if (lane == 0) release(&main_empty[cg & 1]);
             }
             mbar_wait(&corr_full[tl & 1], (tl >> 1) & 1);
             tc_fence_after();
@@ -813,7 +975,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&corr_empty[tl & 1]);           // TMEM released: the rest runs from registers
+            if (lane == 0) release(&corr_empty[tl & 1]);               // TMEM released: the rest runs from registers
 #pragma unroll
             for (int cc = 0; cc < NCH; ++cc) {
                 const int n = nw + cc * 32;
@@ -828,14 +990,15 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     }
     tc_fence_before();
     __syncthreads();
-    if (LNC) {      // neither CTA may exit while its peer can still write into its shared memory
+    if (LNC || PAIR) {      // neither CTA may exit while its peer can still write into its shared memory / arrive on its barriers
         asm volatile("barrier.cluster.arrive.release;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
     }
     if (warp == 1) {
         tc_fence_after();
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
 
@@ -917,13 +1080,14 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [rows, K] fp16 row-major (ld elements), box = 64 (K) x 128 (rows), 128-byte swizzle, zero OOB fill
-static int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld) {
+// [rows, K] fp16 row-major (ld elements), box = 64 (K) x box_rows (128; 64 for the W halves of the PAIR kernels),
+// 128-byte swizzle, zero OOB fill
+static int make_map_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows = TBM) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point unavailable"); return MASR_ERR_INTERNAL; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)TBM};
+    cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -953,6 +1117,7 @@ static int make_map_plane(CUtensorMap* map, const void* ptr, int B, int TH, int 
 //   bit 0  staged (row-contiguous) epilogue stores      ffn_w1 58.5 -> 42.1 us, qkv 35.5 -> 23.5, ctc head 91 -> 63
 //   bit 1  stage the residual READ as well              did not pay (w_2 31 -> 35 us); off
 //   bit 2  16 epilogue warps x 32 columns instead of 8 x 64   ffn_w1 43.1 -> 35.0 us, step 4.88 -> 4.59 ms
+//   bits 5, 6  profiling only (results are garbage): 32 = skip the TMA loads, 64 = skip the MMAs (tools/gemm_bound_probe.py)
 static int tc_flags() {
     const char* e = getenv("MASR_TC_FLAGS");
     return e ? atoi(e) : 5;
@@ -991,10 +1156,56 @@ static int ensure_tc_attrs() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemLn);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<false, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_gemm_kernel<true, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem);
         if (e != cudaSuccess) { set_last_error("tc_gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         g_tc_attr_set[dev] = true;
     }
     return MASR_OK;
+}
+
+// PAIR (cta_group::2) kernels: the default wherever there is more than one row block.  MASR_TC_PAIR=0 keeps the single-CTA
+// kernel (A/B runs: tools/pair_gemm_check.py per GEMM, tools/step_ab.py for the whole step — B200, 32 x 10 s: 3.64 -> 3.54 ms
+// with every GEMM paired; per GEMM the mainloop of a pair tile is ~15 % shorter, the pair's start-up costs ~0.4 us).
+// Needs the 16-epilogue-warp variant (flags bit 2).
+static bool pair_enabled(int flags, int K, int tiles, bool conv) {
+    (void)K; (void)tiles; (void)conv;
+    if (!(flags & 4)) return false;
+    const char* e = getenv("MASR_TC_PAIR");             // read per call: the A/B tools flip it inside one process
+    return e ? atoi(e) != 0 : true;
+}
+
+// Launch a PAIR kernel over `num_ptiles` pair tiles: clusters of 2 CTAs, as many pairs as fit on the device at one CTA per SM.
+template <bool CONV>
+static void launch_pair(const TcMaps& maps, const TcParams& p, int num_ptiles, int tiles_n, int tiles_t, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(tc_threads(16));
+    cfg.dynamicSmemBytes = kTcSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static int max_pairs[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (max_pairs[dev] == 0) {
+        int n = 0;
+        cfg.gridDim = dim3(num_sms() & ~1);
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<CONV, 16, false, true>, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = num_sms() / 2;
+        }
+        max_pairs[dev] = n < num_sms() / 2 ? n : num_sms() / 2;
+    }
+    const int pairs = num_ptiles < max_pairs[dev] ? num_ptiles : max_pairs[dev];
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, tc_gemm_kernel<CONV, 16, false, true>, maps, p, num_ptiles, tiles_n, tiles_t);
 }
 
 }  // namespace masr
@@ -1019,11 +1230,17 @@ extern "C" int masr_conv2_tc_f16x2(const void* c1h, const void* c1l, const void*
         if ((rc = make_map_plane(&maps.a[2 * pl], (const __half*)c1h + pl * plane_elems, B, TH, C))) return rc;
         if ((rc = make_map_plane(&maps.a[2 * pl + 1], (const __half*)c1l + pl * plane_elems, B, TH, C))) return rc;
     }
-    if ((rc = make_map_2d(&maps.w[0], Wh, C, 9 * C, 9 * C))) return rc;
-    if ((rc = make_map_2d(&maps.w[1], Wl, C, 9 * C, 9 * C))) return rc;
+    const bool pair = pair_enabled(tc_flags(), 9 * C, 0, true) && T2 > CONV_TR;
+    if ((rc = make_map_2d(&maps.w[0], Wh, C, 9 * C, 9 * C, pair ? TBN / 2 : TBN))) return rc;
+    if ((rc = make_map_2d(&maps.w[1], Wl, C, 9 * C, 9 * C, pair ? TBN / 2 : TBN))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
     TcParams p{bias, nullptr, out, (__half*)outh, (__half*)outl, 0, C, B * T2 * CONV_W2, C, 9 * C, MASR_EPI_BIAS_RELU, 1.f, T2, tc_flags()};
     const int tiles_n = (C + TBN - 1) / TBN, tiles_t = (T2 + CONV_TR - 1) / CONV_TR;
+    if (pair) {
+        const int ptiles_t = (tiles_t + 1) / 2;
+        launch_pair<true>(maps, p, tiles_n * ptiles_t * B, tiles_n, ptiles_t, (cudaStream_t)stream);
+        return check_launch("tc_gemm_kernel<conv, pair>");
+    }
     const int num_tiles = tiles_n * tiles_t * B;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     if (p.flags & 4) launch_pdl(tc_gemm_kernel<true, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, tiles_t);
@@ -1059,12 +1276,17 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     int rc;
     if ((rc = make_map_2d(&maps.a[0], Ah, M, K, lda))) return rc;
     if ((rc = make_map_2d(&maps.a[1], Al, M, K, lda))) return rc;
-    if ((rc = make_map_2d(&maps.w[0], Wh, N, K, K))) return rc;
-    if ((rc = make_map_2d(&maps.w[1], Wl, N, K, K))) return rc;
+    const bool pair = M > TBM && pair_enabled(tc_flags(), K, ((N + TBN - 1) / TBN) * ((M + TBM - 1) / TBM), false);
+    if ((rc = make_map_2d(&maps.w[0], Wh, N, K, K, pair ? TBN / 2 : TBN))) return rc;
+    if ((rc = make_map_2d(&maps.w[1], Wl, N, K, K, pair ? TBN / 2 : TBN))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
     TcParams p{bias, residual, C, (__half*)Ch, (__half*)Cl, ldr, ldc, M, N, K, epilogue, alpha, 0, tc_flags()};
     if (epilogue == MASR_EPI_RESIDUAL) { p.flags |= preres_flag(residual, ldr, alpha); p.inv_alpha = 1.0f / alpha; }
     const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
+    if (pair) {
+        launch_pair<false>(maps, p, tiles_n * ((tiles_m + 1) / 2), tiles_n, 1, (cudaStream_t)stream);
+        return check_launch("tc_gemm_kernel<pair>");
+    }
     const int num_tiles = tiles_n * tiles_m;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
     if (p.flags & 4) launch_pdl(tc_gemm_kernel<false, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
@@ -1089,8 +1311,9 @@ extern "C" int masr_ctc_head_argmax_tc_f16x2(const void* Ah, const void* Al, int
     int rc;
     if ((rc = make_map_2d(&maps.a[0], Ah, M, K, lda))) return rc;
     if ((rc = make_map_2d(&maps.a[1], Al, M, K, lda))) return rc;
-    if ((rc = make_map_2d(&maps.w[0], Wh, V, K, K))) return rc;
-    if ((rc = make_map_2d(&maps.w[1], Wl, V, K, K))) return rc;
+    const bool pair = M > TBM && pair_enabled(4, K, ((V + TBN - 1) / TBN) * ((M + TBM - 1) / TBM), false);
+    if ((rc = make_map_2d(&maps.w[0], Wh, V, K, K, pair ? TBN / 2 : TBN))) return rc;
+    if ((rc = make_map_2d(&maps.w[1], Wl, V, K, K, pair ? TBN / 2 : TBN))) return rc;
     if ((rc = ensure_tc_attrs())) return rc;
     TcParams p{bias, nullptr, nullptr, nullptr, nullptr, 0, 0, M, V, K, EPI_CTC_PARTIAL, 1.f, 0, tc_flags()};
     p.part_m = (float*)workspace;
@@ -1099,7 +1322,8 @@ extern "C" int masr_ctc_head_argmax_tc_f16x2(const void* Ah, const void* Al, int
     const int tiles_n = (V + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
     const int num_tiles = tiles_n * tiles_m;
     const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-    launch_pdl(tc_gemm_kernel<false, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
+    if (pair) launch_pair<false>(maps, p, tiles_n * ((tiles_m + 1) / 2), tiles_n, 1, (cudaStream_t)stream);
+    else launch_pdl(tc_gemm_kernel<false, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
     if ((rc = check_launch("tc_gemm_kernel<ctc>"))) return rc;
     launch_pdl(ctc_partial_combine_kernel, dim3((M + 31) / 32), dim3(128), 0, (cudaStream_t)stream, (const float*)p.part_m,
                (const float*)p.part_s, (const int*)p.part_i, M, groups, ids, maxp);
