@@ -219,3 +219,31 @@ def test_residual_postln_epilogue(rt, M, K, ada):
     tol = 2e-5 * max(1.0, math.sqrt(K / 256))
     assert (X.cpu() - want_x).abs().max().item() < tol
     assert ((Yh.float() + Yl.float() / 2048.0).cpu() - want_y).abs().max().item() < 2 * tol
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(7936, 2048, 256, 1), (7936, 256, 2048, 5), (385, 264, 320, 0), (129, 4233, 256, 0),
+                                       (2500, 512, 256, 3), (1000, 256, 4864, 4)])
+def test_pair_kernel_bit_identical_to_single_cta(rt, M, N, K, epi, monkeypatch):
+    """The cta_group::2 form (a 256 x 128 tile per pair of CTAs, MMAs issued by the pair's leader, operands in both CTAs'
+    shared memory) computes the same products in the same accumulation order as the single-CTA kernel: every output —
+    fp32, the fp16 (h, l) pair — must be bit-identical, for full tiles, odd row-block counts and ragged column tiles."""
+    g = torch.Generator().manual_seed(7 * M + N + K)
+    Ah, Al = split(rt, torch.randn(M, K, generator=g).to(rt.dev))
+    Wh, Wl = split(rt, (torch.randn(N, K, generator=g) / math.sqrt(K)).to(rt.dev))
+    b = torch.randn(N, generator=g).to(rt.dev)
+    No = N // 2 if epi == 3 else N
+    ldc = (No + 7) // 8 * 8
+    R = torch.randn(M, ldc, generator=g).to(rt.dev) if epi == 5 else None
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MASR_TC_PAIR", mode)
+        C = torch.full((M, ldc), float("nan"), device=rt.dev)
+        Ch = torch.full((M, ldc), float("nan"), dtype=torch.float16, device=rt.dev)
+        Cl = torch.full((M, ldc), float("nan"), dtype=torch.float16, device=rt.dev)
+        rt.call("masr_gemm_tc_f16x2", P(Ah), P(Al), K, P(Wh), P(Wl), P(b), P(R), ldc, P(C), P(Ch), P(Cl), ldc, M, N, K, epi, 0.5, rt.st())
+        torch.cuda.synchronize()
+        outs[mode] = (C, Ch, Cl)
+    for a, c in zip(outs["0"], outs["1"]):
+        assert torch.equal(a[:, :No].view(torch.int32 if a.dtype == torch.float32 else torch.int16),
+                           c[:, :No].view(torch.int32 if c.dtype == torch.float32 else torch.int16))
+    assert torch.isfinite(outs["1"][0][:, :No]).all()

@@ -52,7 +52,9 @@ def time_graph(run):
 
 
 M = 7936
-skip = set(os.environ.get("PROBE_SKIP", "").split(","))       # e.g. "0no_mma,1no_mma"
+# The pair kernel cannot run without loads: the leader would lap the peer CTA's producer on the empty barriers (in the real
+# kernel it cannot consume a stage before the peer's bytes have landed) and the kernel never ends -> skipped by default.
+skip = set(os.environ.get("PROBE_SKIP", "1no_tma,1neither").split(","))
 shapes = set(sys.argv[1:])
 for name, N, K, epi, want_c, want_p, want_r in (("ffn_w2", 256, 2048, 5, True, False, True), ("embed", 256, 4864, 4, True, False, False),
                                                   ("ffn_w1", 2048, 256, 1, False, True, False), ("qkv", 768, 256, 0, True, True, False)):
