@@ -20,6 +20,8 @@
 //            through shared memory -> row-contiguous 128-bit stores (fp32 and/or the fp16 (h,l) pair the next GEMM consumes)
 //   smem ring of 3 x 64 KB stages with full/empty mbarriers; tcgen05.commit releases slots and signals the epilogue.
 //   Launched with programmatic dependent launch: the prologue overlaps the producer kernel's tail.
+// PAIR form (the default): clusters of 2 CTAs own 256 x 128 tiles through tcgen05.mma.cta_group::2 — each CTA
+// stages its 128 A rows and half of the W tile, the pair's leader issues the MMAs and multicasts the commits (4 x 48 KB stages).
 // Round-2 additions: residual epilogues fetch the residual at tile start into the running sum (flags bit 4);
 // EPI_CTC_PARTIAL keeps per (row, 32 columns) softmax partials instead of logits (+ ctc_partial_combine_kernel);
 // the LNC variant (clusters of 2 CTAs) fuses the LayerNorm(s) that follow a residual projection, row statistics over DSMEM
