@@ -135,6 +135,17 @@ int masr_gemm_tc_residual_postln_f16x2(const void* Ah, const void* Al, int64_t l
                                        const float* gamma, const float* beta, const float* ada_scale, const float* ada_bias,
                                        void* Yh, void* Yl, int64_t ldx, int M, int N, int K, float eps, void* stream);
 
+/* LayerNorm + Linear in one launch (K = D = 256): C / (Ch, Cl) = epilogue(LN(x; gamma, beta) . W^T + bias) — the pre-norm
+ * sub-layer inputs: norm_mha -> linear_q/k/v (encoder.py:122, attention.py:72-74), norm_conv -> pointwise_conv1 + GLU
+ * (encoder.py:141, convolution.py:117-118), norm_ff / norm_ff_macaron -> w_1 + SiLU (encoder.py:153/106, positionwise.py:37).
+ * Every CTA (pair) takes a contiguous range of output tiles and first normalises the rows of the <= 2 row blocks that range
+ * touches into (Ah, Al) — an [M, 256] fp16 (h, l) scratch pair the caller provides; on return it holds LN(x) exactly as
+ * masr_layernorm_split_f16 would have written it — then multiplies from it.  epilogue: MASR_EPI_BIAS .. MASR_EPI_BIAS_SCALE.
+ * Same results as masr_layernorm_split_f16 + masr_gemm_tc_f16x2, one launch less. */
+int masr_gemm_tc_lnpre_f16x2(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* Ah, void* Al,
+                             int64_t lda, const void* Wh, const void* Wl, const float* bias, float* C, void* Ch, void* Cl,
+                             int64_t ldc, int M, int N, int K, int epilogue, float alpha, void* stream);
+
 /* CTC head without the [M, V] logits: ctc_lo Linear (loss/ctc.py:70) with a GEMM epilogue that keeps, per frame and per
  * 32-column group, (max logit, first argmax, sum exp(x - max)), then a combine kernel -> per-frame argmax id (first
  * maximum, ctc_greedy_decoder.py:21) and max-probability 1 / sum_j exp(x_j - max) (the softmax value of the argmax).

@@ -240,7 +240,49 @@ struct TcParams {
     float inv_alpha;   // flags bit 4 (residual prefetch): 1 / alpha, exact (alpha is a power of two)
     const float* ada_s;   // EPI_RESIDUAL_POSTLN: optional per-channel scale / bias applied to the LayerNorm output for the pair
     const float* ada_b;
+    // LayerNorm prologue (masr_gemm_tc_lnpre_f16x2, K = 256): the A operand is LayerNorm(lnp_x; ln_g, ln_b) — every CTA
+    // normalises the rows of its own tiles into the pair buffer (lnp_h, lnp_l: the A tensor maps point at it) before loading them
+    const float* lnp_x;
+    int64_t lnp_ldx, lnp_ld;
+    __half* lnp_h;
+    __half* lnp_l;
 };
+
+// One LayerNorm row of width 256 by one warp -> the fp16 (h, l) operand pair.  Lane l holds columns (i*32 + l)*4 .. +3, i = 0, 1:
+// the arithmetic, and its order, of layernorm_kernel<256, true> (norm.cu), so the fused path is bit-identical to the separate one.
+__device__ __forceinline__ void ln_row256_split(const float4 (&v)[2], const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                float eps, int lane, __half* __restrict__ yh, __half* __restrict__ yl) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / 256);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 256) + eps);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        float4 g = ldg_f4(gamma + c), b = ldg_f4(beta + c);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        __half hh[4], ll[4];
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hh[j] = __float2half_rn(ov[j]);
+            ll[j] = __float2half_rn((ov[j] - __half2float(hh[j])) * 2048.0f);
+        }
+        *reinterpret_cast<uint2*>(yh + c) = *reinterpret_cast<const uint2*>(hh);
+        *reinterpret_cast<uint2*>(yl + c) = *reinterpret_cast<const uint2*>(ll);
+    }
+}
 
 // internal epilogue codes (continuing include/masr_b200.h's MASR_EPI_*)
 constexpr int EPI_RESIDUAL_LN = 6, EPI_RESIDUAL_LN2 = 7, EPI_CTC_PARTIAL = 8, EPI_RESIDUAL_POSTLN = 9;
@@ -675,6 +717,13 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
     if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // Tile schedule: CTA (pair) u of U walks tiles u, u + U, ... — or, with the LayerNorm prologue, the contiguous range
+    // [T u / U, T (u + 1) / U) (column tile fastest), so that it needs the rows of at most two row blocks and can normalise
+    // them itself up front.
+    const bool lnp = !LNC && !CONV && p.lnp_x != nullptr;
+    const int tile_begin = lnp ? (int)((int64_t)num_tiles * tile_first / tile_step) : tile_first;
+    const int tile_end = lnp ? (int)((int64_t)num_tiles * (tile_first + 1) / tile_step) : num_tiles;
+    const int tile_stride = lnp ? 1 : tile_step;
     // K <= 256 without a prefetched residual: the "direct" epilogue (TMEM -> registers -> stores, no running sum).
     // (Tried and dropped, tools/step_ab.py: two groups of 8 epilogue warps taking alternate tiles, 64 columns per warp, to
     // overlap the FP32 / MUFU / store phases that 16 warps on one tile run in lockstep -> step +1.4 %, not faster.)
@@ -690,6 +739,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             mbar_init(&main_full[s], 1); mbar_init(&main_empty[s], acc_release);
             mbar_init(&corr_full[s], 1); mbar_init(&corr_empty[s], acc_release);
             if (LNC) mbar_init(&ln_bar[s], 2 * EW);                  // one arrival per epilogue warp of both CTAs
+            else if (lnp) mbar_init(&ln_bar[s], EW);                 // [0]: this CTA's rows are normalised
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -735,7 +785,8 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             constexpr uint32_t a_bytes = CONV ? CONV_ROWS * TBK * 2 : TILE_BYTES;
             constexpr uint32_t tx_bytes = (2 * a_bytes + 2 * R::W_BYTES) * (PAIR ? 2 : 1);   // PAIR: both CTAs' boxes
             uint32_t kg = 0;
-            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+            if (lnp) mbar_wait(&ln_bar[0], 0);      // the epilogue warps have written this CTA's A rows (LayerNorm prologue)
+            for (int tile = tile_begin; tile < tile_end; tile += tile_stride) {
                 int n0, m0, t0, b;
                 decode(tile, n0, m0, t0, b);
                 for (int kb = 0; kb < nkb; ++kb, ++kg) {
@@ -789,7 +840,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             };
             auto commit = [](uint64_t* bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             uint32_t kg = 0, cg = 0, tl = 0;
-            for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++tl) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_stride, ++tl) {
                 mbar_wait(&corr_empty[tl & 1], ((tl >> 1) & 1) ^ 1);    // epilogue has read corr of tile tl-2
                 tc_fence_after();
                 const uint32_t d_corr = tmem_base + 2 * TBN + (tl & 1) * TBN;
@@ -897,8 +948,44 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, TcParams p, int num_tiles, i
             }
             store_chunk<STG, LNC>(p, ctx, v, n, lnx);
         };
+        if (lnp) {
+            // LayerNorm prologue: the 16 epilogue warps normalise this CTA's 128 rows of every row block its tile range touches
+            // (8 rows per warp and block, 4 rows in flight) into the pair buffer the A loads read.  A block shared with the
+            // neighbouring CTA's range is written twice with identical values.
+            if (tile_begin < tile_end) {
+                const int b0 = tile_begin / tiles_n, b1 = (tile_end - 1) / tiles_n;
+                for (int blk = b0; blk <= b1; ++blk) {
+                    const int mrow0 = (blk * (PAIR ? 2 : 1) + (int)crank) * TBM + (warp - 2) * (TBM / EW);
+#pragma unroll
+                    for (int r4 = 0; r4 < TBM / EW; r4 += 4) {
+                        float4 xv[4][2];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int row = mrow0 + r4 + k;
+                            if (row < p.M) {
+                                const float* xr = p.lnp_x + (int64_t)row * p.lnp_ldx;
+                                xv[k][0] = ldg_f4(xr + lane * 4);
+                                xv[k][1] = ldg_f4(xr + (32 + lane) * 4);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int row = mrow0 + r4 + k;
+                            if (row < p.M)                          // warp-uniform
+                                ln_row256_split(xv[k], p.ln_g, p.ln_b, p.ln_eps, lane, p.lnp_h + (int64_t)row * p.lnp_ld,
+                                                p.lnp_l + (int64_t)row * p.lnp_ld);
+                        }
+                    }
+                }
+            }
+            // generic-proxy global writes -> ordered before the TMA loads (async proxy) the producer issues after the barrier
+            __threadfence();
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ln_bar[0]);
+        }
         uint32_t cg = 0, tl = 0;
-        for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++tl) {
+        for (int tile = tile_begin; tile < tile_end; tile += tile_stride, ++tl) {
             int n0, m0, t0, b;
             decode(tile, n0, m0, t0, b);
             const int nw = n0 + cgrp * CW;                             // first column of this warp
@@ -1294,6 +1381,50 @@ extern "C" int masr_gemm_tc_f16x2(const void* Ah, const void* Al, int64_t lda, c
     if (p.flags & 4) launch_pdl(tc_gemm_kernel<false, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
     else launch_pdl(tc_gemm_kernel<false, 8, false>, dim3(grid), dim3(tc_threads(8)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
     return check_launch("tc_gemm_kernel");
+}
+
+// LayerNorm + Linear in one launch (K = D = 256): C / (Ch, Cl) = epilogue(LN(x; gamma, beta) . W^T + bias).
+//   encoder.py:122 -> attention.py:72-74 (norm_mha -> q/k/v), :141 -> convolution.py:117 (norm_conv -> pointwise_conv1 + GLU),
+//   :153 / :106 -> positionwise.py:37 (norm_ff / norm_ff_macaron -> w_1 + SiLU)
+// Every CTA (pair) takes a contiguous range of tiles, normalises the <= 2 row blocks that range touches into the operand
+// pair buffer (Ah, Al: [M, 256] fp16, written here, same values as masr_layernorm_split_f16) and then runs the GEMM on it.
+// Replaces masr_layernorm_split_f16 + masr_gemm_tc_f16x2: one launch and its ~5 us of fill / drain less per LayerNorm.
+extern "C" int masr_gemm_tc_lnpre_f16x2(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* Ah,
+                                        void* Al, int64_t lda, const void* Wh, const void* Wl, const float* bias, float* C,
+                                        void* Ch, void* Cl, int64_t ldc, int M, int N, int K, int epilogue, float alpha,
+                                        void* stream) {
+    if (M == 0 || N == 0) return MASR_OK;
+    MASR_REQUIRE(x && gamma && beta && Ah && Al && Wh && Wl, "masr_gemm_tc_lnpre_f16x2: null pointer");
+    MASR_REQUIRE(C || (Ch && Cl), "masr_gemm_tc_lnpre_f16x2: no output");
+    MASR_REQUIRE((Ch == nullptr) == (Cl == nullptr), "masr_gemm_tc_lnpre_f16x2: Ch/Cl must come as a pair");
+    MASR_REQUIRE(K == 256, "masr_gemm_tc_lnpre_f16x2: K=%d unsupported (the LayerNorm width of this build is 256)", K);
+    MASR_REQUIRE(lda % 8 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                 "masr_gemm_tc_lnpre_f16x2: lda=%lld ldx=%lld alignment", (long long)lda, (long long)ldx);
+    MASR_REQUIRE(epilogue >= MASR_EPI_BIAS && epilogue <= MASR_EPI_BIAS_SCALE, "masr_gemm_tc_lnpre_f16x2: bad epilogue %d", epilogue);
+    MASR_REQUIRE(epilogue != MASR_EPI_BIAS_GLU || N % 32 == 0, "masr_gemm_tc_lnpre_f16x2: GLU epilogue needs N %% 32 == 0");
+    MASR_REQUIRE(ldc % 8 == 0 || (C && !Ch && ldc % 4 == 0), "masr_gemm_tc_lnpre_f16x2: ldc=%lld alignment", (long long)ldc);
+    MASR_REQUIRE(tc_flags() & 4, "masr_gemm_tc_lnpre_f16x2: needs the 16-epilogue-warp kernel (MASR_TC_FLAGS bit 2)");
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc;
+    const int tiles_n = (N + TBN - 1) / TBN, tiles_m = (M + TBM - 1) / TBM;
+    const bool pair = M > TBM && pair_enabled(tc_flags(), K, tiles_n * tiles_m, false);
+    if ((rc = make_map_2d(&maps.a[0], Ah, M, K, lda))) return rc;
+    if ((rc = make_map_2d(&maps.a[1], Al, M, K, lda))) return rc;
+    if ((rc = make_map_2d(&maps.w[0], Wh, N, K, K, pair ? TBN / 2 : TBN))) return rc;
+    if ((rc = make_map_2d(&maps.w[1], Wl, N, K, K, pair ? TBN / 2 : TBN))) return rc;
+    if ((rc = ensure_tc_attrs())) return rc;
+    TcParams p{bias, nullptr, C, (__half*)Ch, (__half*)Cl, 0, ldc, M, N, K, epilogue, alpha, 0, tc_flags()};
+    p.ln_g = gamma; p.ln_b = beta; p.ln_eps = eps;
+    p.lnp_x = x; p.lnp_ldx = ldx; p.lnp_ld = lda; p.lnp_h = (__half*)Ah; p.lnp_l = (__half*)Al;
+    if (pair) {
+        launch_pair<false>(maps, p, tiles_n * ((tiles_m + 1) / 2), tiles_n, 1, (cudaStream_t)stream);
+        return check_launch("tc_gemm_kernel<pair, ln prologue>");
+    }
+    const int num_tiles = tiles_n * tiles_m;
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    launch_pdl(tc_gemm_kernel<false, 16, false>, dim3(grid), dim3(tc_threads(16)), kTcSmem, (cudaStream_t)stream, maps, p, num_tiles, tiles_n, 1);
+    return check_launch("tc_gemm_kernel<ln prologue>");
 }
 
 // ctc_lo Linear + softmax statistics + per-frame argmax (loss/ctc.py:70, ctc_greedy_decoder.py:21-27) without the [M, V]

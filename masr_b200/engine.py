@@ -77,6 +77,9 @@ class ConformerEngine:
         # attention of utterances up to 256 frames on tcgen05 (csrc/attention_tc5.cu); MASR_ATTN=mma keeps the mma.sync kernel
         self.attn_tc5 = os.environ.get("MASR_ATTN", "tc5") != "mma"
         self.fuse = os.environ.get("MASR_FUSE_LN", "0") == "1"
+        # LayerNorm as a PROLOGUE of the GEMM that consumes it (masr_gemm_tc_lnpre_f16x2: norm_mha -> qkv, norm_conv -> pw1,
+        # norm_ff -> w_1): 37 launches fewer per step, results bit-identical.  MASR_FUSE_LNPRE=0/1.
+        self.lnpre = os.environ.get("MASR_FUSE_LNPRE", "0") == "1"
         self.use_graphs = bool(use_graphs)     # replay the batched device step as one CUDA graph per (B, Fmax) shape
         self._graphs = {}
         if not torch.cuda.is_available():
@@ -216,6 +219,18 @@ class ConformerEngine:
             best = min(best, e0.elapsed_time(e1))
         self.launches, self.prof = n0, prof
         return best / (2 * reps)
+
+    def _ln_tc(self, x, gb, yp, W, bias, M, N, epi=EPI_BIAS, C=None, Cp=None, ldc=0, tag="gemm"):
+        """C / Cp = epi(LN(x; gb) . W^T + bias) with yp as the operand pair: one launch (masr_gemm_tc_lnpre_f16x2: every CTA
+        normalises the rows of its own tiles first) when `self.lnpre`, else LayerNorm launch + GEMM launch.  Same results."""
+        d = self.d
+        if self.lnpre and d == 256:
+            self._k(tag, "masr_gemm_tc_lnpre_f16x2", _p(x), d, _p(gb[0]), _p(gb[1]), 1e-5, _p(yp[0]), _p(yp[1]), d, _p(W[0]),
+                    _p(W[1]), _p(bias), _p(C), None if Cp is None else _p(Cp[0]), None if Cp is None else _p(Cp[1]), ldc, M, N, d,
+                    epi, 1.0)
+            return
+        self._ln_split(x, gb, yp, M)
+        self._tc(yp, d, W, bias, M, N, d, epi, C=C, Cp=Cp, ldc=ldc, tag=tag)
 
     def _ln_split(self, x, gb, yp, M):
         self._k("layernorm", "masr_layernorm_split_f16", _p(x), self.d, _p(gb[0]), _p(gb[1]), _p(yp[0]), _p(yp[1]),
@@ -467,23 +482,28 @@ class ConformerEngine:
         for i, L in enumerate(w.layers):
             fuse = self.fuse and d == 256
             if i == 0:                                # later blocks: fused with the previous block's norm_final (below)
-                self._ln_split(x, L.ln_ffm, t0p, M)
-            self._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+                self._ln_tc(x, L.ln_ffm, t0p, tw[i, "ffm1"], L.ffm[1], M, w.ffn, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+            else:
+                self._tc(t0p, d, tw[i, "ffm1"], L.ffm[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
             # every sub-layer's output projection adds into the residual stream AND writes the next sub-layer's LayerNorm-ed
             # operand pair in its epilogue (masr_gemm_tc_residual_ln_f16x2); MASR_FUSE=0: separate LayerNorm launches
             if fuse:
                 self._tc_ln(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, w.ffn, 0.5, x, L.ln_mha, t0p, tag="ffn_w2")
             else:
                 self._tc(hidp, w.ffn, tw[i, "ffm2"], L.ffm[3], M, d, w.ffn, EPI_RESIDUAL, 0.5, x, d, C=x, ldc=d, tag="ffn_w2")
-                self._ln_split(x, L.ln_mha, t0p, M)
-            self._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, Cp=ws["qkvp"], ldc=3 * d, tag="qkv_proj")
+            if fuse:
+                self._tc(t0p, d, tw[i, "qkv"], L.bqkv, M, 3 * d, d, C=qkv, Cp=ws["qkvp"], ldc=3 * d, tag="qkv_proj")
+            else:
+                self._ln_tc(x, L.ln_mha, t0p, tw[i, "qkv"], L.bqkv, M, 3 * d, C=qkv, Cp=ws["qkvp"], ldc=3 * d, tag="qkv_proj")
             self._attention_tc(L, qkv, ws["qkvp"], t1p, T, tlens, B)
             if fuse:
                 self._tc_ln(t1p, d, tw[i, "wo"], L.bo, M, d, 1.0, x, L.ln_conv, t0p, tag="out_proj")
             else:
                 self._tc(t1p, d, tw[i, "wo"], L.bo, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="out_proj")
-                self._ln_split(x, L.ln_conv, t0p, M)
-            self._tc(t0p, d, tw[i, "pw1"], L.pw1_b, M, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d, tag="pw1_glu")
+            if fuse:
+                self._tc(t0p, d, tw[i, "pw1"], L.pw1_b, M, 2 * d, d, EPI_BIAS_GLU, C=g, ldc=d, tag="pw1_glu")
+            else:
+                self._ln_tc(x, L.ln_conv, t0p, tw[i, "pw1"], L.pw1_b, M, 2 * d, EPI_BIAS_GLU, C=g, ldc=d, tag="pw1_glu")
             self._k("dwconv_ln_silu", "masr_dwconv_ln_silu_f32", _p(g), d, T, _p(L.dw), _p(L.dw_b), _p(L.cn[0]),
                     _p(L.cn[1]), _p(L.glu_pad) if self.causal else None, None, _p(t1p[0]), _p(t1p[1]), d, T, _p(tlens), B,
                     d, w.kernel, lpad, T, 1e-5)
@@ -491,8 +511,10 @@ class ConformerEngine:
                 self._tc_ln(t1p, d, tw[i, "pw2"], L.pw2_b, M, d, 1.0, x, L.ln_ff, t0p, tag="pw2")
             else:
                 self._tc(t1p, d, tw[i, "pw2"], L.pw2_b, M, d, d, EPI_RESIDUAL, 1.0, x, d, C=x, ldc=d, tag="pw2")
-                self._ln_split(x, L.ln_ff, t0p, M)
-            self._tc(t0p, d, tw[i, "ff1"], L.ff[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+            if fuse:
+                self._tc(t0p, d, tw[i, "ff1"], L.ff[1], M, w.ffn, d, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
+            else:
+                self._ln_tc(x, L.ln_ff, t0p, tw[i, "ff1"], L.ff[1], M, w.ffn, EPI_BIAS_SILU, Cp=hidp, ldc=w.ffn, tag="ffn_w1")
             # x = norm_final(x + 0.5 ffn), then in the same pass the next consumer's LayerNorm: the next block's
             # norm_ff_macaron (pair only) or, after the last block, after_norm (fp32 encoder output + the CTC head's pair)
             nxt = w.layers[i + 1].ln_ffm if i + 1 < nl else w.after_norm

@@ -247,3 +247,43 @@ def test_pair_kernel_bit_identical_to_single_cta(rt, M, N, K, epi, monkeypatch):
         assert torch.equal(a[:, :No].view(torch.int32 if a.dtype == torch.float32 else torch.int16),
                            c[:, :No].view(torch.int32 if c.dtype == torch.float32 else torch.int16))
     assert torch.isfinite(outs["1"][0][:, :No]).all()
+
+
+@pytest.mark.parametrize("M,N,epi", [(7936, 768, 0), (7936, 2048, 1), (7936, 512, 3), (1000, 768, 0), (129, 2048, 1), (77, 512, 3),
+                                     (385, 4233, 0)])
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_layernorm_prologue_gemm_bit_identical_to_separate_launches(rt, M, N, epi, pair, monkeypatch):
+    """masr_gemm_tc_lnpre_f16x2 (every CTA normalises the rows of its own contiguous tile range, then multiplies) against
+    masr_layernorm_split_f16 + masr_gemm_tc_f16x2: the operand pair it leaves behind and every output must be bit-identical —
+    single-CTA and cta_group::2 kernels, many tiles per CTA, fewer tiles than CTAs, ragged row blocks and column tiles."""
+    monkeypatch.setenv("MASR_TC_PAIR", pair)
+    K = 256
+    g = torch.Generator().manual_seed(M * 3 + N + epi)
+    x = (torch.randn(M, K, generator=g) * 3 + 0.5).to(rt.dev)
+    gamma, beta = (1 + 0.1 * torch.randn(K, generator=g)).to(rt.dev), (0.1 * torch.randn(K, generator=g)).to(rt.dev)
+    Wh, Wl = split(rt, (torch.randn(N, K, generator=g) / math.sqrt(K)).to(rt.dev))
+    b = torch.randn(N, generator=g).to(rt.dev)
+    No = N // 2 if epi == 3 else N
+    ldc = (No + 7) // 8 * 8
+
+    def outs():
+        return (torch.full((M, ldc), float("nan"), device=rt.dev), torch.full((M, ldc), float("nan"), dtype=torch.float16, device=rt.dev),
+                torch.full((M, ldc), float("nan"), dtype=torch.float16, device=rt.dev))
+
+    def pairbuf():
+        return (torch.full((M, K), float("nan"), dtype=torch.float16, device=rt.dev), torch.full((M, K), float("nan"), dtype=torch.float16, device=rt.dev))
+
+    ah, al = pairbuf()
+    C0, Ch0, Cl0 = outs()
+    rt.call("masr_layernorm_split_f16", P(x), K, P(gamma), P(beta), P(ah), P(al), K, M, K, 1e-5, rt.st())
+    rt.call("masr_gemm_tc_f16x2", P(ah), P(al), K, P(Wh), P(Wl), P(b), None, 0, P(C0), P(Ch0), P(Cl0), ldc, M, N, K, epi, 1.0, rt.st())
+    bh, bl = pairbuf()
+    C1, Ch1, Cl1 = outs()
+    rt.call("masr_gemm_tc_lnpre_f16x2", P(x), K, P(gamma), P(beta), 1e-5, P(bh), P(bl), K, P(Wh), P(Wl), P(b), P(C1), P(Ch1), P(Cl1),
+            ldc, M, N, K, epi, 1.0, rt.st())
+    torch.cuda.synchronize()
+    assert torch.equal(ah.view(torch.int16), bh.view(torch.int16)) and torch.equal(al.view(torch.int16), bl.view(torch.int16))
+    assert torch.equal(C0[:, :No].view(torch.int32), C1[:, :No].view(torch.int32))
+    assert torch.equal(Ch0[:, :No].view(torch.int16), Ch1[:, :No].view(torch.int16))
+    assert torch.equal(Cl0[:, :No].view(torch.int16), Cl1[:, :No].view(torch.int16))
+    assert torch.isfinite(C1[:, :No]).all()

@@ -37,6 +37,8 @@ for name, env in variants:
     for k in touched:
         os.environ.pop(k, None)
     os.environ.update(env)
+    eng.lnpre = os.environ.get("MASR_FUSE_LNPRE", "0") == "1"          # engine-level switches are read at construction: refresh
+    eng.fuse = os.environ.get("MASR_FUSE_LN", "0") == "1"
     eng._graphs.clear()
     st = eng.prepare_resident(waves)
     for _ in range(3):
